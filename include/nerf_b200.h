@@ -1,0 +1,169 @@
+/*
+ * nerf_b200.h -- C ABI of the B200-native NeRF render/train hot path.
+ *
+ * This is the drop-in boundary for nerf-dbr's renderer plug-in interface
+ * (reference: src/benchmark/base_renderer.py:90-281).  The reference has no FFI
+ * (it is pure Python), so each entry point below names the reference *method* it
+ * replaces; nerf_dbr_b200/host/ binds them with ctypes (see INTEGRATION.md for the
+ * stub a nerf-dbr maintainer adds).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;  all tensors are dense row-major fp32 unless stated.
+ *   - the caller owns every buffer (inputs, outputs, packed weights); nothing here
+ *     calls cudaMalloc/cudaFree, nothing keeps state between calls -> re-entrant
+ *     across streams and devices.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is enqueued asynchronously on it.
+ *   - return value: 0 = ok, negative = NERF_B200_E* argument error (nothing was
+ *     enqueued), positive = cudaError_t from the launch.  Never throws.
+ *   - there is no CPU fallback: on a machine without an sm_100 device the launch
+ *     fails and the error code is returned.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NERF_B200_API __attribute__((visibility("default")))
+#else
+#define NERF_B200_API
+#endif
+
+#define NERF_B200_ABI_VERSION 1
+
+enum {
+    NERF_B200_OK = 0,
+    NERF_B200_EINVAL = -1,      /* null pointer / non-positive size */
+    NERF_B200_EUNSUPPORTED = -2,/* shape the selected precision mode cannot run */
+    NERF_B200_EALIGN = -3       /* pointer not 16-byte aligned where required */
+};
+
+/* Arithmetic of the MLP contraction. */
+enum {
+    NERF_B200_FP32 = 0,   /* fp32 FFMA on CUDA cores: the <=1e-4 max-abs parity mode */
+    NERF_B200_BF16 = 1    /* bf16 operands, fp32 accumulate in TMEM (tcgen05): the throughput mode */
+};
+
+/* The 22 parameter tensors of one NeRFModel (reference src/models/nerf.py:72-90), as
+ * they sit in its state_dict: nn.Linear weights are [out, in] row-major. */
+typedef struct nerf_b200_params {
+    const float *layer_w[8];   /* [256,63], 3x[256,256], [256,319] (in = [h256, pe63]), 3x[256,256] */
+    const float *layer_b[8];   /* [256] each */
+    const float *density_w;    /* [1,256] */
+    const float *density_b;    /* [1] */
+    const float *color0_w;     /* [128,283] (in = [h256, dir_pe27]) */
+    const float *color0_b;     /* [128] */
+    const float *color1_w;     /* [3,128] */
+    const float *color1_b;     /* [3] */
+} nerf_b200_params;
+
+NERF_B200_API int nerf_b200_abi_version(void);
+NERF_B200_API const char *nerf_b200_error_string(int code);
+
+/* ---- weights -------------------------------------------------------------------------
+ * Replaces the per-renderer weight conversion done in setup()
+ * (pattern: src/benchmark/cpu_optimized_renderer.py:31-52).  `packed` is a caller-owned
+ * device buffer of nerf_b200_packed_bytes() bytes, 1024-byte aligned; it holds the fp32
+ * K-major copies used by the FP32 mode and the bf16 128B-swizzled K-chunks the tcgen05
+ * kernel streams with bulk async copies. */
+NERF_B200_API size_t nerf_b200_packed_bytes(void);
+NERF_B200_API int nerf_b200_pack_weights(const nerf_b200_params *params_host, void *packed, void *stream);
+
+/* ---- rays and samples ------------------------------------------------------------------
+ * generate_rays: BaseUnifiedRenderer.generate_rays (base_renderer.py:223-258; also
+ * NeRFTrainer._get_rays, trainer.py:271-292).  c2w_host = 16 floats, row-major 4x4, read
+ * at call time.  Rows [row0, row0+n_rows) of the H x W image -> rays_o, rays_d
+ * [n_rows*W,3].  Bit-exact with the reference's CPU result. */
+NERF_B200_API int nerf_b200_generate_rays(const float *c2w_host, int width, int height, float focal,
+                            int row0, int n_rows, float *rays_o, float *rays_d, void *stream);
+
+/* sample_points: BaseUnifiedRenderer.sample_points_on_rays (base_renderer.py:260-281);
+ * with t_rand != NULL ([n_rays,n_samples] uniforms) the stratified jitter of
+ * VolumeRenderer.sample_points_on_rays(perturb=True) (src/utils/rendering.py:42-47).
+ * -> points [n_rays,n_samples,3], z_vals [n_rays,n_samples].  Bit-exact. */
+NERF_B200_API int nerf_b200_sample_points(const float *rays_o, const float *rays_d, int n_rays,
+                            int n_samples, float near, float far, const float *t_rand,
+                            float *points, float *z_vals, void *stream);
+
+/* importance_sample: VolumeRenderer.importance_sample (src/utils/rendering.py:54-100) with
+ * the shape fix it needs to run (oracle/nerf_oracle.py:importance_sample).  u [n_rays,n_new]
+ * replaces the internal torch.rand.  -> indices [n_rays,n_new] int64 (searchsorted, right),
+ * z_new [n_rays,n_new], points [n_rays,n_new,3].  n_samples must be a multiple of 32 and
+ * <= 1024.  Bit-exact (indices, depths and points). */
+NERF_B200_API int nerf_b200_importance_sample(const float *rays_o, const float *rays_d, const float *z_vals,
+                                const float *weights, const float *u, int n_rays,
+                                int n_samples, int n_new, int64_t *indices, float *z_new,
+                                float *points, void *stream);
+
+/* ---- network -------------------------------------------------------------------------
+ * positional_encoding: PositionalEncoding.encode (src/models/nerf.py:24-45).
+ * x [n,3] -> out [n, 3+6*n_freq]. */
+NERF_B200_API int nerf_b200_positional_encoding(const float *x, int64_t n, int n_freq, float *out, void *stream);
+
+/* query_network: BaseUnifiedRenderer.query_nerf_networks -> NeRFModel.forward
+ * (base_renderer.py:165-188, src/models/nerf.py:92-131).  positions, directions [n,3] ->
+ * sigma [n,1], rgb [n,3].  mode = NERF_B200_FP32 | NERF_B200_BF16. */
+NERF_B200_API int nerf_b200_query_network(const void *packed, const float *positions, const float *directions,
+                            int64_t n, int mode, float *sigma, float *rgb, void *stream);
+
+/* ---- compositing -----------------------------------------------------------------------
+ * composite: <Renderer>.execute_volume_rendering (src/benchmark/pytorch_renderers.py:105-125)
+ * and VolumeRenderer.volume_render (src/utils/rendering.py:102-143).  sigma [R,S] (the
+ * trailing 1 of [R,S,1] is implicit), rgb [R,S,3], z_vals [R,S], rays_d [R,3] ->
+ * rgb_map [R,3], depth [R]; acc [R] and weights [R,S] when non-NULL. */
+NERF_B200_API int nerf_b200_composite(const float *sigma, const float *rgb, const float *z_vals,
+                        const float *rays_d, int n_rays, int n_samples, float *rgb_map,
+                        float *depth, float *acc, float *weights, void *stream);
+
+/* ---- fused render ------------------------------------------------------------------------
+ * render_image: PyTorchCPURenderer.render_image (src/benchmark/pytorch_renderers.py:127-170):
+ * ray generation, uniform sampling, positional encoding, the fine network and compositing in
+ * ONE kernel; per-sample activations never reach HBM.  Renders rows [row0,row0+n_rows) of the
+ * H x W image (the multi-GPU shard) -> rgb_out [n_rows*W,3], depth_out [n_rows*W]. */
+NERF_B200_API int nerf_b200_render_image(const void *packed, const float *c2w_host, int width, int height,
+                           float focal, float near, float far, int n_samples, int row0,
+                           int n_rows, int mode, float *rgb_out, float *depth_out, void *stream);
+
+/* render_rays: the same fused kernel fed from ray arrays -- the forward of
+ * NeRFTrainer._render_rays (src/training/trainer.py:294-316) for one network, and
+ * _render_ray_chunk of the renderers.  t_rand NULL = uniform depths.  acc_out may be NULL. */
+NERF_B200_API int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *rays_d,
+                          int n_rays, int n_samples, float near, float far, const float *t_rand,
+                          int mode, float *rgb_out, float *depth_out, float *acc_out, void *stream);
+
+/* ---- training ----------------------------------------------------------------------------
+ * train_fwd_bwd: forward + backward of ONE network's term of the photometric loss in
+ * NeRFTrainer.train_step (src/training/trainer.py:117-126):
+ *   loss_term = mean_{R x 3} (C - target)^2,  C = render_rays(...)
+ * d loss/d params is ACCUMULATED (+=) into `grads` (same 22 tensors / shapes as params,
+ * device pointers), scaled by grad_scale / (3 * n_rays_global) * 2 so that data-parallel ranks
+ * can pass their global ray count and all-reduce-sum.  loss_sum (device, 1 float) += sum of
+ * squared errors over this call's rays (divide by 3*R for the mean).  rgb_out [R,3] optional.
+ * workspace: caller-owned, nerf_b200_train_workspace_bytes(n_rays, n_samples) bytes. */
+NERF_B200_API size_t nerf_b200_train_workspace_bytes(int n_rays, int n_samples);
+NERF_B200_API int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params_dev_ptrs_host,
+                            const nerf_b200_params *grads_dev_ptrs_host, const float *rays_o,
+                            const float *rays_d, const float *target, int n_rays, int n_samples,
+                            float near, float far, const float *t_rand, int n_rays_global,
+                            int mode, void *workspace, float *loss_sum, float *rgb_out,
+                            void *stream);
+
+/* ---- introspection (tests / bench) -------------------------------------------------------
+ * Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
+NERF_B200_API uint64_t nerf_b200_launch_count(void);
+/* Optional watchdog word (device, 4 bytes, zero it first; NULL to detach).  The tensor-core kernel's
+ * barrier waits are bounded: on a timeout the kernel stores 0x80000000 | code<<16 | block here and
+ * traps (the launch then fails with a CUDA error instead of hanging the device). */
+NERF_B200_API void nerf_b200_set_watchdog_word(unsigned int *device_word);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,62 @@
+// extern "C" entry points that dispatch on the precision mode (include/nerf_b200.h).
+#include "common.cuh"
+
+namespace nerfb200 {
+int simt_query(const void *, const float *, const float *, long long, float *, float *, cudaStream_t);
+int simt_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, cudaStream_t);
+int simt_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, float *, float *, float *, cudaStream_t);
+int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, float *, float *, float *, unsigned int *, cudaStream_t);
+}
+using namespace nerfb200;
+
+static unsigned int *g_watchdog = nullptr;
+
+extern "C" {
+
+void nerf_b200_set_watchdog_word(unsigned int *device_word) { g_watchdog = device_word; }
+
+int nerf_b200_query_network(const void *packed, const float *positions, const float *directions,
+                            int64_t n, int mode, float *sigma, float *rgb, void *stream)
+{
+    if (!packed || !positions || !directions || !sigma || !rgb || n <= 0) return NERF_B200_EINVAL;
+    if (mode == NERF_B200_FP32) return simt_query(packed, positions, directions, n, sigma, rgb, (cudaStream_t)stream);
+    // per-sample view directions need a per-row colour-0 operand; the tensor-core kernel takes the
+    // direction per ray (render_rays / render_image)
+    return NERF_B200_EUNSUPPORTED;
+}
+
+int nerf_b200_render_image(const void *packed, const float *c2w_host, int width, int height, float focal,
+                           float near, float far, int n_samples, int row0, int n_rows, int mode,
+                           float *rgb_out, float *depth_out, void *stream)
+{
+    if (!packed || !c2w_host || !rgb_out || !depth_out || width <= 0 || height <= 0 || n_samples <= 0 ||
+        n_rows <= 0 || row0 < 0 || row0 + n_rows > height || !(focal > 0.f))
+        return NERF_B200_EINVAL;
+    if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
+    if (mode == NERF_B200_FP32)
+        return simt_render_pose(packed, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows,
+                                rgb_out, depth_out, (cudaStream_t)stream);
+    if (mode == NERF_B200_BF16)
+        return tc_render_pose(packed, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows,
+                              rgb_out, depth_out, g_watchdog, (cudaStream_t)stream);
+    return NERF_B200_EINVAL;
+}
+
+int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
+                          int n_samples, float near, float far, const float *t_rand, int mode,
+                          float *rgb_out, float *depth_out, float *acc_out, void *stream)
+{
+    if (!packed || !rays_o || !rays_d || !rgb_out || !depth_out || n_rays <= 0 || n_samples <= 0)
+        return NERF_B200_EINVAL;
+    if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
+    if (mode == NERF_B200_FP32)
+        return simt_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, rgb_out,
+                                depth_out, acc_out, (cudaStream_t)stream);
+    if (mode == NERF_B200_BF16)
+        return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, rgb_out,
+                              depth_out, acc_out, g_watchdog, (cudaStream_t)stream);
+    return NERF_B200_EINVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,338 @@
+// HBM-bound helper kernels: ray generation, sample placement, inverse-CDF importance
+// sampling, positional encoding, and standalone alpha compositing.
+//
+// Rays, depths, points and importance indices are BIT-EXACT with the reference's torch-CPU
+// results (recipes: common.cuh, mirrored from oracle/scalar_oracle.c); writes are coalesced
+// and vectorised (one float4 store per thread for the 16 B/sample point stream).
+#include "common.cuh"
+
+namespace nerfb200 {
+
+unsigned long long g_launches = 0;
+
+// ------------------------------------------------------------------------------ rays
+// one thread per output float: e -> (ray, component).  reference base_renderer.py:223-258
+__global__ void generate_rays_kernel(Pose pose, int width, int row0, int n_rows, float half_w,
+                                     float half_h, float focal, float *__restrict__ rays_o,
+                                     float *__restrict__ rays_d)
+{
+    size_t total = (size_t)n_rows * width * 3;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        uint32_t ray = (uint32_t)(e / 3), c = (uint32_t)(e - (size_t)ray * 3);
+        int j = row0 + (int)(ray / (uint32_t)width), i = (int)(ray % (uint32_t)width);
+        float dx, dy;
+        pixel_dir(i, j, half_w, half_h, focal, dx, dy);
+        rays_d[e] = rotate_dir(pose, (int)c, dx, dy);
+        rays_o[e] = pose.t[c];
+    }
+}
+
+// ------------------------------------------------------------------------------ samples
+// points [R,S,3] as a flat float stream, one float4 (16 B) store per thread-iteration;
+// z_vals [R,S] likewise.  reference base_renderer.py:260-281, rendering.py:17-52
+__global__ void sample_points_kernel(const float *__restrict__ rays_o,
+                                     const float *__restrict__ rays_d, uint32_t n_rays,
+                                     uint32_t n_samples, float near, float far,
+                                     const float *__restrict__ t_rand,
+                                     float *__restrict__ points, float *__restrict__ z_vals)
+{
+    extern __shared__ float z_tab[];   // uniform depths, shared by every ray
+    const float step = linspace_step((int)n_samples);
+    for (uint32_t s = threadIdx.x; s < n_samples; s += blockDim.x)
+        z_tab[s] = depth_uniform((int)s, (int)n_samples, step, near, far);
+    __syncthreads();
+
+    const size_t n_smp = (size_t)n_rays * n_samples;
+    const size_t n_pt4 = (n_smp * 3 + 3) / 4, n_z4 = (n_smp + 3) / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    auto depth_of = [&](size_t smp, uint32_t s) -> float {
+        if (t_rand == nullptr) return z_tab[s];
+        float lo = z_tab[s], hi = z_tab[s];
+        if (s > 0) lo = __fmul_rn(0.5f, __fadd_rn(z_tab[s], z_tab[s - 1]));
+        if (s + 1 < n_samples) hi = __fmul_rn(0.5f, __fadd_rn(z_tab[s + 1], z_tab[s]));
+        return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), __ldg(t_rand + smp)));
+    };
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n_pt4; q += stride) {
+        size_t e = q * 4;
+        size_t smp = e / 3;
+        uint32_t c = (uint32_t)(e - smp * 3);
+        uint32_t ray = (uint32_t)(smp / n_samples), s = (uint32_t)(smp - (size_t)ray * n_samples);
+        float v[4];
+        float z = depth_of(smp, s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = 0.0f;
+            if (smp < n_smp)
+                v[i] = point_on_ray(__ldg(rays_o + (size_t)ray * 3 + c), __ldg(rays_d + (size_t)ray * 3 + c), z);
+            if (++c == 3) {
+                c = 0; ++smp;
+                if (++s == n_samples) { s = 0; ++ray; }
+                if (smp < n_smp) z = depth_of(smp, s);
+            }
+        }
+        if (e + 4 <= n_smp * 3) {
+            reinterpret_cast<float4 *>(points)[q] = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int i = 0; i < 4 && e + i < n_smp * 3; ++i) points[e + i] = v[i];
+        }
+    }
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n_z4; q += stride) {
+        size_t smp = q * 4;
+        uint32_t ray = (uint32_t)(smp / n_samples), s = (uint32_t)(smp - (size_t)ray * n_samples);
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = (smp + i < n_smp) ? depth_of(smp + i, s) : 0.0f;
+            if (++s == n_samples) s = 0;
+        }
+        if (smp + 4 <= n_smp) {
+            reinterpret_cast<float4 *>(z_vals)[q] = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int i = 0; i < 4 && smp + i < n_smp; ++i) z_vals[smp + i] = v[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ importance
+// one warp per ray.  reference rendering.py:73-95 (+ shape fix); recipe SURVEY A5-A7:
+//   total = torch.sum(w+1e-5): lane l accumulates elements l, l+32, ... ; lanes l, l+8, l+16,
+//   l+24 are combined ((a0+a1)+a2)+a3; the 8 results are added 0..7.
+//   cdf = running DOUBLE sum of fl(w/total), rounded to fp32 per element (serial: exact order).
+__global__ void importance_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                  const float *__restrict__ z_vals, const float *__restrict__ weights,
+                                  const float *__restrict__ u, int n_rays, int n_samples, int n_new,
+                                  long long *__restrict__ indices, float *__restrict__ z_new,
+                                  float *__restrict__ points)
+{
+    extern __shared__ float smem[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *cdf = smem + (size_t)warp * (2 * n_samples + 2);   // [S+1]
+    float *zs = cdf + n_samples + 1;                          // [S]
+    for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
+        const float *w = weights + (size_t)ray * n_samples;
+        float part = 0.0f;
+        for (int s = lane; s < n_samples; s += 32) {
+            float v = __fadd_rn(__ldg(w + s), 1e-5f);
+            cdf[s + 1] = v;                                    // park w+1e-5
+            zs[s] = __ldg(z_vals + (size_t)ray * n_samples + s);
+            part = __fadd_rn(part, v);
+        }
+        float a1 = __shfl_sync(0xffffffffu, part, (lane & 7) + 8);
+        float a2 = __shfl_sync(0xffffffffu, part, (lane & 7) + 16);
+        float a3 = __shfl_sync(0xffffffffu, part, (lane & 7) + 24);
+        float a0 = __shfl_sync(0xffffffffu, part, (lane & 7));
+        float l8 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+        float total = __shfl_sync(0xffffffffu, l8, 0);
+#pragma unroll
+        for (int l = 1; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, l8, l));
+        __syncwarp();
+        if (lane == 0) {
+            double run = 0.0;
+            cdf[0] = 0.0f;
+            for (int s = 0; s < n_samples; ++s) {
+                run += (double)__fdiv_rn(cdf[s + 1], total);
+                cdf[s + 1] = (float)run;
+            }
+        }
+        __syncwarp();
+        const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
+        const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
+        for (int k = lane; k < n_new; k += 32) {
+            size_t o = (size_t)ray * n_new + k;
+            float uk = __ldg(u + o);
+            int lo = 0, hi = n_samples + 1;                    // first index with cdf > u (right=True)
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= uk) lo = mid + 1; else hi = mid; }
+            int below = min(max(lo - 1, 0), n_samples - 1), above = min(lo, n_samples - 1);
+            float den = __fsub_rn(cdf[above], cdf[below]);
+            if (den < 1e-5f) den = 1.0f;
+            float t = __fdiv_rn(__fsub_rn(uk, cdf[below]), den);
+            float z = __fadd_rn(zs[below], __fmul_rn(t, __fsub_rn(zs[above], zs[below])));
+            indices[o] = lo;
+            z_new[o] = z;
+            points[3 * o + 0] = point_on_ray(ox, dx, z);
+            points[3 * o + 1] = point_on_ray(oy, dy, z);
+            points[3 * o + 2] = point_on_ray(oz, dz, z);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------ encoding
+// one thread per output float.  reference nerf.py:24-45: arg = fl(fl(2^k*pi) * x), full-range sinf/cosf
+__global__ void encode_kernel(const float *__restrict__ x, size_t n, int n_freq, float *__restrict__ out)
+{
+    const uint32_t width = 3 + 6 * n_freq;
+    const size_t total = n * width;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+        size_t row = e / width;
+        uint32_t j = (uint32_t)(e - row * width);
+        float r;
+        if (j < 3) {
+            r = __ldg(x + row * 3 + j);
+        } else {
+            uint32_t k = (j - 3) / 6, w = (j - 3) - 6 * k, c = w % 3;
+            float arg = __fmul_rn(kPiF * (float)(1u << k), __ldg(x + row * 3 + c));
+            r = (w < 3) ? sinf(arg) : cosf(arg);
+        }
+        out[e] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------ compositing
+// One warp per ray; lanes take 32 consecutive samples per step, the transmittance is an
+// exclusive prefix product carried across steps in double (the reference's CPU cumprod keeps
+// a double running product).  reference pytorch_renderers.py:105-125, rendering.py:117-141
+__device__ __forceinline__ double warp_incl_prod(double v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v *= n;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void composite_kernel(const float *__restrict__ sigma, const float *__restrict__ rgb,
+                                 const float *__restrict__ z_vals, const float *__restrict__ rays_d,
+                                 int n_rays, int n_samples, float *__restrict__ rgb_map,
+                                 float *__restrict__ depth, float *__restrict__ acc,
+                                 float *__restrict__ weights)
+{
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
+        const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        const size_t base = (size_t)ray * n_samples;
+        double carry = 1.0;
+        float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+        for (int s0 = 0; s0 < n_samples; s0 += 32) {
+            int s = s0 + lane;
+            bool on = s < n_samples;
+            float z = on ? __ldg(z_vals + base + s) : 0.f;
+            float zn = (s + 1 < n_samples) ? __ldg(z_vals + base + s + 1) : 0.f;
+            float dist = __fmul_rn((s + 1 < n_samples) ? __fsub_rn(zn, z) : 1e10f, nrm);
+            float sg = on ? fmaxf(__ldg(sigma + base + s), 0.f) : 0.f;
+            float alpha = on ? __fsub_rn(1.0f, expf(__fmul_rn(-sg, dist))) : 0.f;
+            float keep = on ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+            double incl = warp_incl_prod((double)keep, lane);
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            float trans = (float)(carry * (lane == 0 ? 1.0 : excl));
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
+            float w = __fmul_rn(alpha, trans);
+            if (on) {
+                cr = fmaf(w, __ldg(rgb + 3 * (base + s) + 0), cr);
+                cg = fmaf(w, __ldg(rgb + 3 * (base + s) + 1), cg);
+                cb = fmaf(w, __ldg(rgb + 3 * (base + s) + 2), cb);
+                cd = fmaf(w, z, cd);
+                ca += w;
+                if (weights) weights[base + s] = w;
+            }
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); cd = warp_sum(cd); ca = warp_sum(ca);
+        if (lane == 0) {
+            rgb_map[3 * ray + 0] = cr; rgb_map[3 * ray + 1] = cg; rgb_map[3 * ray + 2] = cb;
+            depth[ray] = cd;
+            if (acc) acc[ray] = ca;
+        }
+    }
+}
+
+static inline int grid_for(size_t work_items, int block, int per_sm = 8)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t want = (work_items + block - 1) / block;
+    size_t cap = (size_t)sms * per_sm;            // a whole number of waves of resident CTAs
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace nerfb200
+
+using namespace nerfb200;
+
+extern "C" {
+
+int nerf_b200_abi_version(void) { return NERF_B200_ABI_VERSION; }
+
+uint64_t nerf_b200_launch_count(void) { return g_launches; }
+
+const char *nerf_b200_error_string(int code)
+{
+    if (code == 0) return "ok";
+    if (code == NERF_B200_EINVAL) return "invalid argument (null pointer or non-positive size)";
+    if (code == NERF_B200_EUNSUPPORTED) return "shape not supported by the selected mode";
+    if (code == NERF_B200_EALIGN) return "pointer not 16-byte aligned";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown nerf_b200 error";
+}
+
+int nerf_b200_generate_rays(const float *c2w_host, int width, int height, float focal, int row0,
+                            int n_rows, float *rays_o, float *rays_d, void *stream)
+{
+    if (!c2w_host || !rays_o || !rays_d || width <= 0 || height <= 0 || n_rows <= 0 || row0 < 0 ||
+        row0 + n_rows > height || !(focal > 0.f))
+        return NERF_B200_EINVAL;
+    size_t total = (size_t)n_rows * width * 3;
+    generate_rays_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        pose_from_c2w(c2w_host), width, row0, n_rows, (float)((double)width * 0.5),
+        (float)((double)height * 0.5), focal, rays_o, rays_d);
+    return launch_status();
+}
+
+int nerf_b200_sample_points(const float *rays_o, const float *rays_d, int n_rays, int n_samples,
+                            float near, float far, const float *t_rand, float *points,
+                            float *z_vals, void *stream)
+{
+    if (!rays_o || !rays_d || !points || !z_vals || n_rays <= 0 || n_samples <= 0) return NERF_B200_EINVAL;
+    if (n_samples > 8192) return NERF_B200_EUNSUPPORTED;
+    if (((uintptr_t)points | (uintptr_t)z_vals) & 15) return NERF_B200_EALIGN;
+    size_t units = ((size_t)n_rays * n_samples * 3 + 3) / 4;
+    sample_points_kernel<<<grid_for(units, 256), 256, n_samples * sizeof(float), (cudaStream_t)stream>>>(
+        rays_o, rays_d, (uint32_t)n_rays, (uint32_t)n_samples, near, far, t_rand, points, z_vals);
+    return launch_status();
+}
+
+int nerf_b200_importance_sample(const float *rays_o, const float *rays_d, const float *z_vals,
+                                const float *weights, const float *u, int n_rays, int n_samples,
+                                int n_new, int64_t *indices, float *z_new, float *points, void *stream)
+{
+    if (!rays_o || !rays_d || !z_vals || !weights || !u || !indices || !z_new || !points ||
+        n_rays <= 0 || n_samples <= 0 || n_new <= 0)
+        return NERF_B200_EINVAL;
+    if (n_samples % 32 != 0 || n_samples > 1024) return NERF_B200_EUNSUPPORTED;
+    const int block = 128;
+    size_t smem = (size_t)(block / 32) * (2 * n_samples + 2) * sizeof(float);
+    importance_kernel<<<grid_for((size_t)n_rays * 32, block), block, smem, (cudaStream_t)stream>>>(
+        rays_o, rays_d, z_vals, weights, u, n_rays, n_samples, n_new, (long long *)indices, z_new, points);
+    return launch_status();
+}
+
+int nerf_b200_positional_encoding(const float *x, int64_t n, int n_freq, float *out, void *stream)
+{
+    if (!x || !out || n <= 0 || n_freq < 0 || n_freq > 16) return NERF_B200_EINVAL;
+    size_t total = (size_t)n * (3 + 6 * n_freq);
+    encode_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, n_freq, out);
+    return launch_status();
+}
+
+int nerf_b200_composite(const float *sigma, const float *rgb, const float *z_vals, const float *rays_d,
+                        int n_rays, int n_samples, float *rgb_map, float *depth, float *acc,
+                        float *weights, void *stream)
+{
+    if (!sigma || !rgb || !z_vals || !rays_d || !rgb_map || !depth || n_rays <= 0 || n_samples <= 0)
+        return NERF_B200_EINVAL;
+    composite_kernel<<<grid_for((size_t)n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        sigma, rgb, z_vals, rays_d, n_rays, n_samples, rgb_map, depth, acc, weights);
+    return launch_status();
+}
+
+}  // extern "C"

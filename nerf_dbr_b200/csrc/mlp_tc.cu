@@ -1,0 +1,623 @@
+// BF16 mode: the fused render kernel on 5th-generation tensor cores.
+//
+//   rays -> uniform/stratified depths -> positional encoding -> 8x256 MLP (+ heads) -> alpha
+//   compositing, one persistent CTA per SM, per-sample activations never leave the SM.
+//
+// Per 128-sample tile the CTA runs nine GEMMs as tcgen05.mma (M=128, N=256|128, K=16 bf16,
+// fp32 accumulators in TMEM):  L0 (K=64: encoded position), L1-L3 (K=256), L4 (K=64 encoded
+// position + K=256 hidden -- the skip is a second accumulate, not a concat), L5-L7, C0 (N=128).
+//   * A operand: activations written by the epilogue warps as bf16 into shared memory, in place,
+//     in the 128B-swizzled K-major canonical layout (4 K-blocks of [128 x 64]).
+//   * B operand: weight K-chunks ([N x 64] bf16, pre-swizzled by pack.cu) streamed L2 -> shared
+//     memory with cp.async.bulk (the TMA engine) through a 3-stage mbarrier ring.
+//   * D: two 256-column TMEM accumulators alternate per layer, so the MMA of layer l+1 starts on
+//     K-block 0 as soon as the epilogue has rewritten that K-block, while the epilogue is still
+//     reading the rest of layer l's accumulator.
+//   * The view direction enters colour layer 0 as an fp32 per-ray bias (W_dir . enc(d) + b),
+//     computed once per ray on CUDA cores: no per-sample direction encoding at all.
+//   * density head (256 FMAs/row) and the 128->3 colour output run in the epilogue from the fp32
+//     accumulators; compositing is a segmented warp scan (transmittance products) by the
+//     front/back warps, which also generate the next tile's rays, depths and encodings.
+//
+// Warp roles (512 threads): 0 weight producer | 1 MMA issuer | 2 TMEM allocator | 4-11 epilogue
+// (lane quadrant = warp % 4, column half = (warp-4)/4) | 12-15 front (encode) / back (composite).
+//
+// reference: PyTorchCPURenderer.render_image / _render_ray_chunk (src/benchmark/
+// pytorch_renderers.py:127-170), NeRFModel.forward (src/models/nerf.py:92-131),
+// execute_volume_rendering (pytorch_renderers.py:105-125).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nerfb200 {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kThreads = 512;
+constexpr int kTileM = 128;
+constexpr int kWStages = 3;
+constexpr uint32_t kWStageBytes = 32768;
+constexpr int kChunksPerTile = 34;
+constexpr int kMaxRaysPerTile = 8;      // S_pad >= 16
+
+// shared memory map (bytes from a 1024-aligned base)
+constexpr uint32_t SM_A = 0;                               // 4 x [128 x 64] bf16
+constexpr uint32_t SM_PE = 65536;                          // 2 x [128 x 64] bf16
+constexpr uint32_t SM_W = 98304;                           // kWStages x 32 KB
+constexpr uint32_t SM_BIAS = SM_W + kWStages * kWStageBytes;   // [8][256] f32
+constexpr uint32_t SM_WSIG = SM_BIAS + 8192;               // [256] f32
+constexpr uint32_t SM_WC1 = SM_WSIG + 1024;                // [3][128] f32
+constexpr uint32_t SM_RAYB = SM_WC1 + 1536;                // [2][8][128] f32  per-ray colour-0 bias
+constexpr uint32_t SM_FIN = SM_RAYB + 8192;                // [2][128][8] f32  per-row head partials
+constexpr uint32_t SM_DE = SM_FIN + 8192;                  // [8][32] f32      direction encodings
+constexpr uint32_t SM_SCR = SM_DE + 1024;                  // back-warp scratch (256 B)
+constexpr uint32_t SM_BAR = SM_SCR + 256;                  // mbarriers
+constexpr uint32_t SM_TMEM = SM_BAR + 256;
+constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+constexpr uint32_t kSmemBytes = SM_TOTAL + 1024;           // + alignment slack
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// barrier indices
+enum { B_WFULL = 0, B_WEMPTY = 3, B_PEFULL = 6, B_PEEMPTY = 8, B_AREADY = 10, B_ACCFULL = 14,
+       B_FINFULL = 16, B_FINEMPTY = 18, B_COUNT = 20 };
+
+// chunk consumption order per tile: index into the packed chunk stream (packed_layout.h).
+// K-blocks of a layer are consumed 0,2,1,3 (both column halves of the previous epilogue finish
+// their first K-block at the same time); layer 4 takes its encoded-position chunk first, because
+// that operand does not wait for the previous epilogue.
+__constant__ uint8_t kOrder[kChunksPerTile] = {
+    0,                 // L0
+    1, 3, 2, 4,        // L1
+    5, 7, 6, 8,        // L2
+    9, 11, 10, 12,     // L3
+    17, 13, 15, 14, 16,// L4 (pe, h0, h2, h1, h3)
+    18, 20, 19, 21,    // L5
+    22, 24, 23, 25,    // L6
+    26, 28, 27, 29,    // L7
+    30, 32, 31, 33};   // C0
+// which A K-block a chunk multiplies: 0..3 = hidden K-block, 4 = encoded-position tile
+__constant__ uint8_t kASrc[kChunksPerTile] = {
+    4, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 4, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3};
+__constant__ uint8_t kLayerChunks[9] = {1, 4, 4, 4, 5, 4, 4, 4, 4};
+
+enum { SRC_RAYS = 1, SRC_POSE = 2 };
+
+struct Args {
+    const unsigned char *packed;
+    Pose pose;
+    int width, row0;
+    float half_w, half_h, focal;
+    const float *rays_o, *rays_d, *t_rand;
+    int n_rays, n_samples;
+    int s_pad_log2;            // S_pad = 1 << s_pad_log2 when tiles_per_ray == 1
+    int tiles_per_ray;         // > 1 when S_pad > 128
+    int n_tiles, tiles_per_cta;
+    float near, far;
+    float *rgb_map, *depth, *acc;
+    unsigned int *dbg;         // optional: [0] = first timeout code
+};
+
+constexpr long long kTimeoutCycles = 4000000000LL;
+
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, unsigned int *dbg, uint32_t code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kTimeoutCycles) {
+            if (dbg) atomicCAS(dbg, 0u, 0x80000000u | (code << 16) | (blockIdx.x & 0xffffu));
+            __trap();
+        }
+    }
+}
+
+struct RowInfo { int ray, s; bool valid; };
+
+__device__ __forceinline__ RowInfo row_info(const Args &a, int tile, int row)
+{
+    RowInfo r;
+    if (a.tiles_per_ray == 1) {
+        int rpt_log2 = 7 - a.s_pad_log2;
+        r.ray = (tile << rpt_log2) + (row >> a.s_pad_log2);
+        r.s = row & ((1 << a.s_pad_log2) - 1);
+    } else {
+        r.ray = tile / a.tiles_per_ray;
+        r.s = (tile - r.ray * a.tiles_per_ray) * kTileM + row;
+    }
+    r.valid = r.ray < a.n_rays && r.s < a.n_samples;
+    return r;
+}
+
+template <int SRC>
+__device__ __forceinline__ void ray_of(const Args &a, int ray, float (&o)[3], float (&d)[3])
+{
+    if (SRC == SRC_POSE) {
+        int j = a.row0 + ray / a.width, i = ray % a.width;
+        float dx, dy;
+        pixel_dir(i, j, a.half_w, a.half_h, a.focal, dx, dy);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { d[c] = rotate_dir(a.pose, c, dx, dy); o[c] = a.pose.t[c]; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { d[c] = __ldg(a.rays_d + 3 * (size_t)ray + c); o[c] = __ldg(a.rays_o + 3 * (size_t)ray + c); }
+    }
+}
+
+__device__ __forceinline__ float depth_of(const Args &a, int ray, int s, float step)
+{
+    return a.t_rand ? depth_jittered(s, a.n_samples, step, a.near, a.far, __ldg(a.t_rand + (size_t)ray * a.n_samples + s))
+                    : depth_uniform(s, a.n_samples, step, a.near, a.far);
+}
+
+// phase of fl(pi_f * x) in units of 2^-32 turns.  All ten frequencies are exact left shifts of it:
+// fl(fl(2^k pi) x) == 2^k fl(pi_f x) because scaling by 2^k commutes with rounding.
+__device__ __forceinline__ uint32_t phase_of(float x)
+{
+    float arg = __fmul_rn(kPiF, x);
+    double turns = (double)arg * 0.15915494309189535;
+    return (uint32_t)(long long)__double2ll_rn(turns * 4294967296.0);
+}
+__device__ __forceinline__ void sincos_phase(uint32_t phase, float &s, float &c)
+{
+    float r = (float)(int)phase * 1.4629180792671596e-9f;    // 2 pi / 2^32, r in [-pi, pi)
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
+// ------------------------------------------------------------------------------------------
+// front: rays, depths, points, encoded-position tile (bf16, swizzled) and per-ray colour bias
+template <int SRC>
+__device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pb, int row, float step,
+                             const float *__restrict__ wf)
+{
+    RowInfo ri = row_info(a, tile, row);
+    float feat[64];
+#pragma unroll
+    for (int f = 0; f < 64; ++f) feat[f] = 0.f;
+    if (ri.valid) {
+        float o[3], d[3];
+        ray_of<SRC>(a, ri.ray, o, d);
+        float z = depth_of(a, ri.ray, ri.s, step);
+        uint32_t ph[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float p = point_on_ray(o[c], d[c], z);
+            feat[c] = p;
+            ph[c] = phase_of(p);
+        }
+#pragma unroll
+        for (int k = 0; k < kPosFreq; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float sn, cs;
+                sincos_phase(ph[c] << k, sn, cs);
+                feat[3 + 6 * k + c] = sn;
+                feat[3 + 6 * k + 3 + c] = cs;
+            }
+    }
+    const uint32_t pe_row = smem_u32(sm + SM_PE + pb * 16384 + row * 128);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        st_shared_v4(pe_row + ((u ^ (row & 7)) << 4),
+                     pack_bf16(feat[8 * u + 0], feat[8 * u + 1]), pack_bf16(feat[8 * u + 2], feat[8 * u + 3]),
+                     pack_bf16(feat[8 * u + 4], feat[8 * u + 5]), pack_bf16(feat[8 * u + 6], feat[8 * u + 7]));
+
+    // direction encodings of the tile's rays: thread (q*32 + f) -> feature f of ray q (fp32, full-range sinf/cosf)
+    const int rpt = a.tiles_per_ray == 1 ? (kTileM >> a.s_pad_log2) : 1;
+    float *de = reinterpret_cast<float *>(sm + SM_DE);
+    for (int q = row >> 5, f = row & 31; q < rpt; q += 4) {
+        {
+            int ray = a.tiles_per_ray == 1 ? tile * rpt + q : tile / a.tiles_per_ray;
+            float v = 0.f;
+            if (ray < a.n_rays && f < kDirFeat) {
+                float o[3], d[3];
+                ray_of<SRC>(a, ray, o, d);
+                if (f < 3) v = d[f];
+                else {
+                    int k = (f - 3) / 6, w = (f - 3) - 6 * k, c = w % 3;
+                    float arg = __fmul_rn(kPiF * (float)(1 << k), d[c]);
+                    v = w < 3 ? sinf(arg) : cosf(arg);
+                }
+            }
+            de[q * 32 + f] = v;
+        }
+    }
+    named_bar_sync(1, 128);
+    float *rayb = reinterpret_cast<float *>(sm + SM_RAYB) + pb * (kMaxRaysPerTile * 128);
+    for (int q = 0; q < rpt; ++q) {
+        float acc = __ldg(wf + F_BC0 + row);
+#pragma unroll
+        for (int j = 0; j < kDirFeat; ++j) acc = fmaf(de[q * 32 + j], __ldg(wf + F_WC0D + j * 128 + row), acc);
+        rayb[q * 128 + row] = acc;
+    }
+    named_bar_sync(1, 128);          // de[] is rewritten by the next produce
+}
+
+// ------------------------------------------------------------------------------------------
+// back: sigmoid / relu heads, alpha, segmented transmittance scan, weighted sums, output
+template <int SRC>
+__device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int row, float step,
+                               const float *__restrict__ wf, uint32_t bar_fin_empty)
+{
+    const int lane = row & 31, warp = row >> 5;
+    const float4 *fin = reinterpret_cast<const float4 *>(sm + SM_FIN + fb * 4096 + row * 32);
+    float4 f0 = fin[0], f1 = fin[1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_fin_empty);           // partials are in registers
+
+    RowInfo ri = row_info(a, tile, row);
+    float sigma = fmaxf(f0.x + f0.y + __ldg(wf + F_BSIG), 0.f);
+    float col[3];
+    col[0] = 1.0f / (1.0f + expf(-(f0.z + f1.y + __ldg(wf + F_BC1 + 0))));
+    col[1] = 1.0f / (1.0f + expf(-(f0.w + f1.z + __ldg(wf + F_BC1 + 1))));
+    col[2] = 1.0f / (1.0f + expf(-(f1.x + f1.w + __ldg(wf + F_BC1 + 2))));
+    float alpha = 0.f, keep = 1.f, z = 0.f;
+    if (ri.valid) {
+        float o[3], d[3];
+        ray_of<SRC>(a, ri.ray, o, d);
+        float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+        z = depth_of(a, ri.ray, ri.s, step);
+        float dz = 1e10f;
+        if (ri.s + 1 < a.n_samples) dz = __fsub_rn(depth_of(a, ri.ray, ri.s + 1, step), z);
+        float dist = __fmul_rn(dz, dn);
+        alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, dist)));
+        keep = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    }
+    // segmented inclusive product scan over rows of one ray
+    const int seg = a.tiles_per_ray == 1 ? (1 << a.s_pad_log2) : kTileM;   // rows per ray in this tile
+    const int wseg = seg < 32 ? seg : 32;
+    float incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (o < wseg && (lane & (wseg - 1)) >= o) incl *= n;
+    }
+    float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    float trans = (lane & (wseg - 1)) == 0 ? 1.0f : prev;
+    float *scr = reinterpret_cast<float *>(sm + SM_SCR);          // [0..3] warp products, [4..9] carry, [16..] sums
+    float *carry = scr + 4;
+    if (seg > 32) {
+        if (lane == 31) scr[warp] = incl;
+        named_bar_sync(1, 128);
+        const int w0 = seg >= kTileM ? 0 : (warp & ~1);           // first warp of this ray's segment
+        float pre = 1.0f;
+        for (int w = w0; w < warp; ++w) pre *= scr[w];
+        if (a.tiles_per_ray > 1 && (tile % a.tiles_per_ray) != 0) pre *= carry[0];
+        trans *= pre;
+    }
+    float w = __fmul_rn(alpha, trans);
+    float sums[5] = {w * col[0], w * col[1], w * col[2], w * z, w};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        if (o < wseg) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sums[i] += __shfl_xor_sync(0xffffffffu, sums[i], o);
+        }
+    if (seg <= 32) {
+        if ((lane & (wseg - 1)) == 0 && ri.ray < a.n_rays) {
+            a.rgb_map[3 * (size_t)ri.ray + 0] = sums[0]; a.rgb_map[3 * (size_t)ri.ray + 1] = sums[1];
+            a.rgb_map[3 * (size_t)ri.ray + 2] = sums[2];
+            a.depth[ri.ray] = sums[3];
+            if (a.acc) a.acc[ri.ray] = sums[4];
+        }
+    } else {
+        float *ws = scr + 16 + warp * 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) ws[i] = sums[i];
+        }
+        named_bar_sync(1, 128);
+        const int wpr = seg >> 5;                                 // warps per ray: 2 or 4
+        if (lane == 0 && (warp & (wpr - 1)) == 0 && ri.ray < a.n_rays) {
+            float t[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                t[i] = 0.f;
+                for (int k = 0; k < wpr; ++k) t[i] += scr[16 + (warp + k) * 5 + i];
+            }
+            bool first = true, last = true;
+            if (a.tiles_per_ray > 1) {
+                int part = tile % a.tiles_per_ray;
+                first = part == 0; last = part == a.tiles_per_ray - 1;
+                if (!first) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) t[i] += carry[1 + i];
+                }
+                float prod = scr[0] * scr[1] * scr[2] * scr[3];
+                carry[0] = first ? prod : carry[0] * prod;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) carry[1 + i] = t[i];
+            }
+            if (last) {
+                a.rgb_map[3 * (size_t)ri.ray + 0] = t[0]; a.rgb_map[3 * (size_t)ri.ray + 1] = t[1];
+                a.rgb_map[3 * (size_t)ri.ray + 2] = t[2];
+                a.depth[ri.ray] = t[3];
+                if (a.acc) a.acc[ri.ray] = t[4];
+            }
+        }
+        named_bar_sync(1, 128);      // scratch reused by the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int SRC>
+__global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm_base = smem_u32(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bars = sm_base + SM_BAR;
+    auto bar = [&](int i) { return bars + 8u * i; };
+    const float *wf = reinterpret_cast<const float *>(a.packed);
+    const unsigned char *wb = a.packed + B_OFFSET;
+
+    const int tile_begin = blockIdx.x * a.tiles_per_cta;
+    const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_cta);
+    const int my_tiles = max(0, tile_end - tile_begin);
+
+    // ---- one-time setup -------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWStages; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
+            mbar_init(bar(B_ACCFULL + i), 1);
+            mbar_init(bar(B_FINFULL + i), 8); mbar_init(bar(B_FINEMPTY + i), 4);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), 4);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<512>(sm_base + SM_TMEM);
+    {   // small fp32 tables the epilogue reads as shared-memory broadcasts
+        float *bias = reinterpret_cast<float *>(sm + SM_BIAS);
+        for (int i = threadIdx.x; i < 8 * 256; i += kThreads) bias[i] = __ldg(wf + F_BIAS + i);
+        float *wsig = reinterpret_cast<float *>(sm + SM_WSIG);
+        for (int i = threadIdx.x; i < 256; i += kThreads) wsig[i] = __ldg(wf + F_WSIG + i);
+        float *wc1 = reinterpret_cast<float *>(sm + SM_WC1);
+        for (int i = threadIdx.x; i < 384; i += kThreads) wc1[i] = __ldg(wf + F_WC1 + i);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_TMEM);
+
+    if (warp == 0) {
+        // ================================ weight producer ===================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int c = 0; c < kChunksPerTile; ++c, ++it) {
+                    const uint32_t stage = it % kWStages, round = it / kWStages;
+                    if (round > 0) wait_bar(bar(B_WEMPTY + stage), (round - 1) & 1, a.dbg, 1);
+                    const int ci = kOrder[c];
+                    const uint32_t bytes = ci < kChunks256 ? (uint32_t)kChunkBytes256 : (uint32_t)kChunkBytes128;
+                    const unsigned char *src = ci < kChunks256 ? wb + (size_t)ci * kChunkBytes256
+                                                               : wb + B_C0 + (size_t)(ci - kChunks256) * kChunkBytes128;
+                    mbar_arrive_expect_tx(bar(B_WFULL + stage), bytes);
+                    bulk_g2s(sm_base + SM_W + stage * kWStageBytes, src, bytes, bar(B_WFULL + stage));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer =========================================
+        if (lane == 0) {
+            uint32_t it = 0, g = 0, a_uses = 0;     // a_uses: completed uses of each a_ready barrier
+            const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
+            for (int t = 0; t < my_tiles; ++t) {
+                const int pb = t & 1;
+                wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 2);
+                int c = 0;
+                for (int layer = 0; layer < 9; ++layer, ++g) {
+                    const uint32_t d_tmem = tmem_base + (g & 1) * 256;
+                    const uint32_t idesc = layer == 8 ? idesc128 : idesc256;
+                    const int nch = kLayerChunks[layer];
+                    for (int j = 0; j < nch; ++j, ++c, ++it) {
+                        const int asrc = kASrc[c];
+                        uint32_t a_addr;
+                        if (asrc == 4) a_addr = sm_base + SM_PE + pb * 16384;
+                        else {
+                            a_addr = sm_base + SM_A + asrc * 16384;
+                            wait_bar(bar(B_AREADY + asrc), a_uses & 1, a.dbg, 3);
+                        }
+                        const uint32_t stage = it % kWStages;
+                        wait_bar(bar(B_WFULL + stage), (it / kWStages) & 1, a.dbg, 4);
+                        tc_fence_after_sync();
+                        const uint64_t adesc = smem_desc_sw128(a_addr);
+                        const uint64_t bdesc = smem_desc_sw128(sm_base + SM_W + stage * kWStageBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)      // 4 x (K = 16): +32 B inside the 128 B swizzle span
+                            mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | k) != 0);
+                        mma_commit(bar(B_WEMPTY + stage));
+                    }
+                    mma_commit(bar(B_ACCFULL + (g & 1)));
+                    if (layer == 4) mma_commit(bar(B_PEEMPTY + pb));
+                    if (layer >= 1) ++a_uses;         // layers 1..8 consumed one phase of every a_ready[kb]
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ================================ epilogue ===========================================
+        const int ew = warp - 4, q = ew & 3, hf = ew >> 2;
+        const int row = q * 32 + lane;
+        const float *bias_s = reinterpret_cast<const float *>(sm + SM_BIAS);
+        const float *wsig_s = reinterpret_cast<const float *>(sm + SM_WSIG);
+        const float *wc1_s = reinterpret_cast<const float *>(sm + SM_WC1);
+        const uint32_t a_row = sm_base + SM_A + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7);
+        uint32_t g = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int pb = t & 1, fb = t & 1;
+            float *fin = reinterpret_cast<float *>(sm + SM_FIN + fb * 4096 + row * 32);
+            for (int layer = 0; layer < 9; ++layer, ++g) {
+                wait_bar(bar(B_ACCFULL + (g & 1)), (g >> 1) & 1, a.dbg, 5);
+                tc_fence_after_sync();
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256;
+                if (layer < 8) {
+                    float sig = 0.f;
+#pragma unroll 1
+                    for (int grp = 0; grp < 4; ++grp) {
+                        const int col0 = hf * 128 + grp * 32;
+                        uint32_t v[32];
+                        tmem_ld32(t_acc + col0, v);
+                        tmem_ld_wait();
+                        const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + layer * 256 + col0);
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 b = b4[i];
+                            float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+                            float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+                            pk[2 * i + 0] = relu_pack_bf16(x0, x1);
+                            pk[2 * i + 1] = relu_pack_bf16(x2, x3);
+                            if (layer == 7) {
+                                float4 w4 = reinterpret_cast<const float4 *>(wsig_s + col0)[i];
+                                sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
+                                sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
+                            }
+                        }
+                        const int kb = col0 >> 6, u0 = (col0 & 63) >> 3;      // 4 x 16-byte units of K-block kb
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            st_shared_v4(a_row + kb * 16384 + (((u0 + u) ^ swz) << 4),
+                                         pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                        if (grp & 1) {                                        // a K-block of the next A operand is complete
+                            tc_fence_before_sync();
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar(B_AREADY + kb));
+                        }
+                    }
+                    if (layer == 7) {
+                        if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
+                        fin[hf] = sig;
+                    }
+                } else {
+                    // colour layer 0 (N = 128): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
+                    wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
+                    const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
+                    const float *rb = reinterpret_cast<const float *>(sm + SM_RAYB) + pb * (kMaxRaysPerTile * 128) +
+                                      (row >> rpt_shift) * 128;
+                    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+                    for (int grp = 0; grp < 2; ++grp) {
+                        const int col0 = hf * 64 + grp * 32;
+                        uint32_t v[32];
+                        tmem_ld32(t_acc + col0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 b = reinterpret_cast<const float4 *>(rb + col0)[i];
+                            float4 w0 = reinterpret_cast<const float4 *>(wc1_s + col0)[i];
+                            float4 w1 = reinterpret_cast<const float4 *>(wc1_s + 128 + col0)[i];
+                            float4 w2 = reinterpret_cast<const float4 *>(wc1_s + 256 + col0)[i];
+                            float x0 = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), x1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+                            float x2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), x3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
+                            r0 = fmaf(x0, w0.x, r0); r0 = fmaf(x1, w0.y, r0); r0 = fmaf(x2, w0.z, r0); r0 = fmaf(x3, w0.w, r0);
+                            r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
+                            r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
+                        }
+                    }
+                    fin[2 + 3 * hf + 0] = r0; fin[2 + 3 * hf + 1] = r1; fin[2 + 3 * hf + 2] = r2;
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_FINFULL + fb));
+                }
+            }
+        }
+    } else if (warp >= 12) {
+        // ================================ front / back =======================================
+        const int row = (warp - 12) * 32 + lane;
+        const float step = linspace_step(a.n_samples);
+        auto produce = [&](int t) {
+            const int pb = t & 1;
+            if (t >= 2) wait_bar(bar(B_PEEMPTY + pb), ((t >> 1) - 1) & 1, a.dbg, 8);
+            produce_tile<SRC>(a, sm, tile_begin + t, pb, row, step, wf);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_PEFULL + pb));
+        };
+        if (my_tiles > 0) produce(0);
+        for (int t = 0; t < my_tiles; ++t) {
+            if (t + 1 < my_tiles) produce(t + 1);
+            const int fb = t & 1;
+            wait_bar(bar(B_FINFULL + fb), (t >> 1) & 1, a.dbg, 9);
+            composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, bar(B_FINEMPTY + fb));
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static int plan(Args &a)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int S = a.n_samples;
+    if (S < 1 || S > 32768) return NERF_B200_EUNSUPPORTED;
+    if (S <= kTileM) {
+        int lg = 4;                                   // S_pad >= 16 (at most 8 rays per tile)
+        while ((1 << lg) < S) ++lg;
+        a.s_pad_log2 = lg;
+        a.tiles_per_ray = 1;
+        int rpt = kTileM >> lg;
+        a.n_tiles = (a.n_rays + rpt - 1) / rpt;
+    } else {
+        a.s_pad_log2 = 7;
+        a.tiles_per_ray = (S + kTileM - 1) / kTileM;
+        a.n_tiles = a.n_rays * a.tiles_per_ray;
+    }
+    int per = (a.n_tiles + sms - 1) / sms;
+    per = ((per + a.tiles_per_ray - 1) / a.tiles_per_ray) * a.tiles_per_ray;   // a ray never straddles CTAs
+    a.tiles_per_cta = per;
+    return (a.n_tiles + per - 1) / per;               // grid
+}
+
+template <int SRC>
+static int launch(Args &a, cudaStream_t stream)
+{
+    int grid = plan(a);
+    if (grid < 0) return grid;
+    cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    fused_render_kernel<SRC><<<grid, kThreads, kSmemBytes, stream>>>(a);
+    return launch_status();
+}
+
+}  // namespace tc
+
+int tc_render_pose(const void *packed, const float *c2w, int width, int height, float focal, float near,
+                   float far, int n_samples, int row0, int n_rows, float *rgb_out, float *depth_out,
+                   unsigned int *dbg, cudaStream_t stream)
+{
+    tc::Args a = {};
+    a.packed = reinterpret_cast<const unsigned char *>(packed);
+    a.pose = pose_from_c2w(c2w);
+    a.width = width; a.row0 = row0;
+    a.half_w = (float)((double)width * 0.5); a.half_h = (float)((double)height * 0.5); a.focal = focal;
+    a.n_rays = n_rows * width; a.n_samples = n_samples;
+    a.near = near; a.far = far;
+    a.rgb_map = rgb_out; a.depth = depth_out; a.acc = nullptr; a.dbg = dbg;
+    return tc::launch<tc::SRC_POSE>(a, stream);
+}
+
+int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples,
+                   float near, float far, const float *t_rand, float *rgb_out, float *depth_out,
+                   float *acc_out, unsigned int *dbg, cudaStream_t stream)
+{
+    tc::Args a = {};
+    a.packed = reinterpret_cast<const unsigned char *>(packed);
+    a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
+    a.n_rays = n_rays; a.n_samples = n_samples;
+    a.near = near; a.far = far;
+    a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
+    return tc::launch<tc::SRC_RAYS>(a, stream);
+}
+
+}  // namespace nerfb200

@@ -1,0 +1,89 @@
+// Weight packing: 22 fp32 state-dict tensors -> the packed buffer of packed_layout.h.
+// Runs once per checkpoint in setup() (reference pattern: cpu_optimized_renderer.py:31-52).
+#include "common.cuh"
+
+namespace nerfb200 {
+
+struct ChunkSrc { const float *w; int ld; int k0; int k_valid; };   // rows n, columns k0..k0+63
+
+// source of bf16 chunk `ci` (0..29: N=256 chunks, 30..33: colour-0 N=128 chunks)
+__device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int ci)
+{
+    if (ci == 0) return {p.layer_w[0], 63, 0, 63};
+    if (ci <= 12) { int l = 1 + (ci - 1) / 4, kc = (ci - 1) % 4; return {p.layer_w[l], 256, kc * 64, 64}; }
+    if (ci <= 16) return {p.layer_w[4], 319, (ci - 13) * 64, 64};
+    if (ci == 17) return {p.layer_w[4], 319, 256, 63};
+    if (ci <= 29) { int l = 5 + (ci - 18) / 4, kc = (ci - 18) % 4; return {p.layer_w[l], 256, kc * 64, 64}; }
+    return {p.color0_w, 283, (ci - 30) * 64, 64};
+}
+
+__global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ packed)
+{
+    float *f = reinterpret_cast<float *>(packed);
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+
+    // ---- fp32 region ----
+    for (size_t i = tid; i < F_END; i += nth) {
+        float v = 0.f;
+        if (i < F_WSIG) { int l = (int)(i / 256), n = (int)(i % 256); v = p.layer_b[l][n]; }
+        else if (i < F_BSIG) v = p.density_w[i - F_WSIG];
+        else if (i < F_BC0) v = (i == F_BSIG) ? p.density_b[0] : 0.f;
+        else if (i < F_WC1) v = p.color0_b[i - F_BC0];
+        else if (i < F_BC1) v = p.color1_w[i - F_WC1];
+        else if (i < F_W0T) v = (i - F_BC1 < 3) ? p.color1_b[i - F_BC1] : 0.f;
+        else if (i < F_WT) { size_t j = i - F_W0T; int k = (int)(j / 256), n = (int)(j % 256); v = k < 63 ? p.layer_w[0][n * 63 + k] : 0.f; }
+        else if (i < F_W4P) {
+            size_t j = i - F_WT; int l = 1 + (int)(j / 65536); j %= 65536;
+            int k = (int)(j / 256), n = (int)(j % 256);
+            v = p.layer_w[l][(size_t)n * (l == 4 ? 319 : 256) + k];
+        }
+        else if (i < F_WC0H) { size_t j = i - F_W4P; int k = (int)(j / 256), n = (int)(j % 256); v = k < 63 ? p.layer_w[4][n * 319 + 256 + k] : 0.f; }
+        else if (i < F_WC0D) { size_t j = i - F_WC0H; int k = (int)(j / 128), n = (int)(j % 128); v = p.color0_w[n * 283 + k]; }
+        else { size_t j = i - F_WC0D; int k = (int)(j / 128), n = (int)(j % 128); v = k < 27 ? p.color0_w[n * 283 + 256 + k] : 0.f; }
+        f[i] = v;
+    }
+
+    // ---- bf16 region: one 16-byte unit (8 consecutive k of one row) per thread-iteration ----
+    const size_t units256 = (size_t)kChunks256 * 256 * 8, units = units256 + (size_t)kChunks128 * 128 * 8;
+    for (size_t uidx = tid; uidx < units; uidx += nth) {
+        int ci, n, unit; size_t chunk_off;
+        if (uidx < units256) { ci = (int)(uidx / 2048); n = (int)((uidx % 2048) / 8); unit = (int)(uidx % 8); chunk_off = (size_t)ci * kChunkBytes256; }
+        else { size_t r = uidx - units256; ci = 30 + (int)(r / 1024); n = (int)((r % 1024) / 8); unit = (int)(r % 8); chunk_off = B_C0 + (size_t)(ci - 30) * kChunkBytes128; }
+        ChunkSrc src = chunk_source(p, ci);
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int k = unit * 8 + j;
+            float w = k < src.k_valid ? src.w[(size_t)n * src.ld + src.k0 + k] : 0.f;
+            hi[j] = __float2bfloat16_rn(w);
+            lo[j] = __float2bfloat16_rn(w - __bfloat162float(hi[j]));
+        }
+        size_t off = chunk_off + swz128((uint32_t)n, (uint32_t)unit * 8);
+        *reinterpret_cast<uint4 *>(packed + B_OFFSET + off) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
+    }
+}
+
+}  // namespace nerfb200
+
+using namespace nerfb200;
+
+extern "C" {
+
+size_t nerf_b200_packed_bytes(void) { return PACKED_BYTES; }
+
+int nerf_b200_pack_weights(const nerf_b200_params *params_host, void *packed, void *stream)
+{
+    if (!params_host || !packed) return NERF_B200_EINVAL;
+    const nerf_b200_params &p = *params_host;
+    for (int l = 0; l < 8; ++l)
+        if (!p.layer_w[l] || !p.layer_b[l]) return NERF_B200_EINVAL;
+    if (!p.density_w || !p.density_b || !p.color0_w || !p.color0_b || !p.color1_w || !p.color1_b)
+        return NERF_B200_EINVAL;
+    if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
+    pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<unsigned char *>(packed));
+    return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""B200Renderer -- the CUDA renderer that sits alongside PyTorch MPS/CPU/CUDA, NumPy+Numba,
+CPU-Optimized and Compressed in nerf-dbr's benchmark (src/benchmark/), loading the same
+checkpoint and answering the same calls, backed by libnerf_b200.so.
+
+Registration mirrors ``PyTorchCUDARenderer`` (src/benchmark/pytorch_renderers.py:173-178): the
+constructor raises RuntimeError when CUDA is unavailable, so the suite's try/except skips it
+(src/benchmark/benchmark_suite.py:88-92).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import lib as L
+from . import ops
+
+try:  # inside a nerf-dbr checkout: be a subclass of the reference's own base class
+    from src.benchmark.base_renderer import BaseUnifiedRenderer as _Base  # type: ignore
+except Exception:  # standalone
+    from .base_renderer import BaseUnifiedRenderer as _Base
+
+
+class B200Renderer(_Base):
+    """precision = 'bf16' (tcgen05 tensor cores, the throughput mode) or 'fp32' (CUDA-core FFMA,
+    max-abs <= 1e-4 against PyTorchCPURenderer)."""
+
+    def __init__(self, precision: str = "bf16", device_index: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA not available on this system")
+        L.load_library()                       # raises if the CUDA library was not built
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        self.mode = L.BF16 if precision == "bf16" else L.FP32
+        self.device_index = device_index
+        super().__init__(f"B200 {precision.upper()}", "cuda")
+        self._torch_device = torch.device("cuda", device_index)
+        self._packed = {}
+
+    # ---- setup: load the shared checkpoint, pack both networks once ---------------------------
+    def setup(self, checkpoint_path: str):
+        super().setup(checkpoint_path)
+        coarse, fine = self.shared_model.get_models(self.device)
+        self._packed = {"coarse": ops.pack_weights(coarse, self._torch_device),
+                        "fine": ops.pack_weights(fine, self._torch_device)}
+
+    def _net(self, use_fine: bool = True) -> torch.Tensor:
+        if not self._packed:
+            raise RuntimeError("Models not loaded. Call setup() first.")
+        return self._packed["fine" if use_fine else "coarse"]
+
+    # ---- the reference interface -----------------------------------------------------------------
+    def generate_rays(self, camera_pose, width: int, height: int, focal: float = 800.0):
+        """[H,W,3] origins and directions (base_renderer.py:223-258), bit-exact."""
+        return ops.generate_rays(camera_pose, width, height, focal, device=self._torch_device)
+
+    def sample_points_on_rays(self, rays_o, rays_d, n_samples: int = 64):
+        """points [R,S,3], z_vals [R,S] (base_renderer.py:260-281), bit-exact."""
+        return ops.sample_points(rays_o.to(self._torch_device), rays_d.to(self._torch_device), n_samples,
+                                 self.near, self.far)
+
+    def query_nerf_networks(self, positions, directions, use_fine: bool = True):
+        """(density [N,1], rgb [N,3]) (base_renderer.py:165-188).  Per-sample directions run in the
+        FP32 kernel; the tensor-core kernel takes directions per ray (render_image)."""
+        return ops.query_network(self._net(use_fine), positions.to(self._torch_device),
+                                 directions.to(self._torch_device), L.FP32)
+
+    def execute_volume_rendering(self, densities, colors, z_vals, ray_directions) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(rgb_map [R,3], depth_map [R]) (pytorch_renderers.py:105-125)."""
+        sigma = densities[..., 0] if densities.dim() == 3 else densities
+        return ops.composite(sigma.to(self._torch_device), colors.to(self._torch_device),
+                             z_vals.to(self._torch_device), ray_directions.to(self._torch_device))
+
+    def render_image(self, camera_pose, resolution: Tuple[int, int], samples_per_ray: int = 64):
+        """(rgb [H,W,3], depth [H,W]) device tensors: one fused kernel launch, fine network, uniform
+        samples (pytorch_renderers.py:127-170)."""
+        width, height = resolution
+        return ops.render_image(self._net(True), camera_pose, width, height, samples_per_ray, self.mode,
+                                800.0, self.near, self.far)
+
+    def render_rows(self, camera_pose, resolution: Tuple[int, int], samples_per_ray: int, row0: int, n_rows: int,
+                    out_rgb=None, out_depth=None):
+        """The multi-GPU shard: rows [row0, row0+n_rows) of the image."""
+        width, height = resolution
+        return ops.render_image(self._net(True), camera_pose, width, height, samples_per_ray, self.mode,
+                                800.0, self.near, self.far, row0, n_rows, out_rgb, out_depth)

@@ -1,0 +1,186 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and the
+current CUDA stream.  Every function requires CUDA tensors (fp32, contiguous) -- no CPU path."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as L
+from .model import STATE_ORDER
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise L.NerfB200Error(name, -101, "expected a CUDA tensor (nerf_dbr_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _c2w(pose: torch.Tensor):
+    flat = pose.detach().to("cpu", torch.float32).reshape(-1)
+    if flat.numel() != 16:
+        raise ValueError("camera_pose must be 4x4")
+    return (ctypes.c_float * 16)(*flat.tolist())
+
+
+def params_struct(tensors: dict) -> L.Params:
+    """nerf_b200_params from a name -> CUDA tensor mapping (state-dict names)."""
+    p = L.Params()
+    for i in range(8):
+        p.layer_w[i] = tensors[f"layers.{i}.weight"].data_ptr()
+        p.layer_b[i] = tensors[f"layers.{i}.bias"].data_ptr()
+    p.density_w = tensors["density_head.weight"].data_ptr()
+    p.density_b = tensors["density_head.bias"].data_ptr()
+    p.color0_w = tensors["color_layers.0.weight"].data_ptr()
+    p.color0_b = tensors["color_layers.0.bias"].data_ptr()
+    p.color1_w = tensors["color_layers.1.weight"].data_ptr()
+    p.color1_b = tensors["color_layers.1.bias"].data_ptr()
+    return p
+
+
+def pack_weights(model_or_state, device: Optional[torch.device] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pack one network's 22 tensors (nn.Module or state dict) into the kernel layout."""
+    lib = L.load_library()
+    sd = model_or_state.state_dict() if hasattr(model_or_state, "state_dict") else model_or_state
+    if device is None:
+        device = next(iter(sd.values())).device
+        if device.type != "cuda":
+            device = torch.device("cuda", torch.cuda.current_device())
+    keep = {k: sd[k].detach().to(device, torch.float32).contiguous() for k in STATE_ORDER}
+    nbytes = lib.nerf_b200_packed_bytes()
+    if out is None:
+        out = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-out.data_ptr()) % 1024
+    view = out[off:off + nbytes]
+    p = params_struct(keep)
+    with torch.cuda.device(device):
+        L.check("nerf_b200_pack_weights", lib.nerf_b200_pack_weights(ctypes.byref(p), _ptr(view), _stream()))
+    view._keepalive = (out, keep)      # the pack kernel is asynchronous
+    return view
+
+
+def generate_rays(pose: torch.Tensor, width: int, height: int, focal: float = 800.0, row0: int = 0,
+                  n_rows: Optional[int] = None, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = L.load_library()
+    n_rows = height - row0 if n_rows is None else n_rows
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    ro = torch.empty(n_rows, width, 3, device=device)
+    rd = torch.empty(n_rows, width, 3, device=device)
+    with torch.cuda.device(device):
+        L.check("nerf_b200_generate_rays", lib.nerf_b200_generate_rays(
+            _c2w(pose), width, height, focal, row0, n_rows, _ptr(ro), _ptr(rd), _stream()))
+    return ro, rd
+
+
+def sample_points(rays_o: torch.Tensor, rays_d: torch.Tensor, n_samples: int, near: float = 2.0,
+                  far: float = 6.0, t_rand: Optional[torch.Tensor] = None):
+    lib = L.load_library()
+    ro, rd = _dev(rays_o, "sample_points"), _dev(rays_d, "sample_points")
+    n = ro.shape[0]
+    pts = torch.empty(n, n_samples, 3, device=ro.device)
+    z = torch.empty(n, n_samples, device=ro.device)
+    tr = None if t_rand is None else _dev(t_rand, "sample_points")
+    with torch.cuda.device(ro.device):
+        L.check("nerf_b200_sample_points", lib.nerf_b200_sample_points(
+            _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), _ptr(pts), _ptr(z), _stream()))
+    return pts, z
+
+
+def importance_sample(rays_o, rays_d, z_vals, weights, u):
+    lib = L.load_library()
+    ro, rd, z, w, u = (_dev(t, "importance_sample") for t in (rays_o, rays_d, z_vals, weights, u))
+    n, s = z.shape
+    k = u.shape[1]
+    idx = torch.empty(n, k, dtype=torch.int64, device=z.device)
+    zn = torch.empty(n, k, device=z.device)
+    pts = torch.empty(n, k, 3, device=z.device)
+    with torch.cuda.device(z.device):
+        L.check("nerf_b200_importance_sample", lib.nerf_b200_importance_sample(
+            _ptr(ro), _ptr(rd), _ptr(z), _ptr(w), _ptr(u), n, s, k, _ptr(idx), _ptr(zn), _ptr(pts), _stream()))
+    return pts, zn, idx
+
+
+def positional_encoding(x: torch.Tensor, n_freq: int) -> torch.Tensor:
+    lib = L.load_library()
+    x = _dev(x, "positional_encoding")
+    out = torch.empty(x.shape[0], 3 + 6 * n_freq, device=x.device)
+    if x.shape[0] == 0:
+        return out
+    with torch.cuda.device(x.device):
+        L.check("nerf_b200_positional_encoding", lib.nerf_b200_positional_encoding(
+            _ptr(x), x.shape[0], n_freq, _ptr(out), _stream()))
+    return out
+
+
+def query_network(packed: torch.Tensor, positions: torch.Tensor, directions: torch.Tensor,
+                  mode: int = L.FP32):
+    lib = L.load_library()
+    pos, dirs = _dev(positions, "query_network"), _dev(directions, "query_network")
+    n = pos.shape[0]
+    sigma = torch.empty(n, 1, device=pos.device)
+    rgb = torch.empty(n, 3, device=pos.device)
+    with torch.cuda.device(pos.device):
+        L.check("nerf_b200_query_network", lib.nerf_b200_query_network(
+            _ptr(packed), _ptr(pos), _ptr(dirs), n, mode, _ptr(sigma), _ptr(rgb), _stream()))
+    return sigma, rgb
+
+
+def composite(sigma, rgb, z_vals, rays_d, want_aux: bool = False):
+    lib = L.load_library()
+    sg, col, z, rd = (_dev(t, "composite") for t in (sigma, rgb, z_vals, rays_d))
+    n, s = z.shape
+    rgb_map = torch.empty(n, 3, device=z.device)
+    depth = torch.empty(n, device=z.device)
+    acc = torch.empty(n, device=z.device) if want_aux else None
+    wts = torch.empty(n, s, device=z.device) if want_aux else None
+    with torch.cuda.device(z.device):
+        L.check("nerf_b200_composite", lib.nerf_b200_composite(
+            _ptr(sg), _ptr(col), _ptr(z), _ptr(rd), n, s, _ptr(rgb_map), _ptr(depth), _ptr(acc), _ptr(wts), _stream()))
+    return (rgb_map, depth, acc, wts) if want_aux else (rgb_map, depth)
+
+
+def render_image(packed: torch.Tensor, pose: torch.Tensor, width: int, height: int, n_samples: int,
+                 mode: int = L.BF16, focal: float = 800.0, near: float = 2.0, far: float = 6.0,
+                 row0: int = 0, n_rows: Optional[int] = None, out_rgb=None, out_depth=None):
+    lib = L.load_library()
+    n_rows = height - row0 if n_rows is None else n_rows
+    dev = packed.device
+    rgb = out_rgb if out_rgb is not None else torch.empty(n_rows, width, 3, device=dev)
+    depth = out_depth if out_depth is not None else torch.empty(n_rows, width, device=dev)
+    with torch.cuda.device(dev):
+        L.check("nerf_b200_render_image", lib.nerf_b200_render_image(
+            _ptr(packed), _c2w(pose), width, height, focal, near, far, n_samples, row0, n_rows, mode,
+            _ptr(rgb), _ptr(depth), _stream()))
+    return rgb, depth
+
+
+def render_rays(packed: torch.Tensor, rays_o, rays_d, n_samples: int, mode: int = L.BF16,
+                near: float = 2.0, far: float = 6.0, t_rand=None, want_acc: bool = False):
+    lib = L.load_library()
+    ro, rd = _dev(rays_o, "render_rays"), _dev(rays_d, "render_rays")
+    n = ro.shape[0]
+    rgb = torch.empty(n, 3, device=ro.device)
+    depth = torch.empty(n, device=ro.device)
+    acc = torch.empty(n, device=ro.device) if want_acc else None
+    tr = None if t_rand is None else _dev(t_rand, "render_rays")
+    with torch.cuda.device(ro.device):
+        L.check("nerf_b200_render_rays", lib.nerf_b200_render_rays(
+            _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), mode,
+            _ptr(rgb), _ptr(depth), _ptr(acc), _stream()))
+    return (rgb, depth, acc) if want_acc else (rgb, depth)
+
+
+def launch_count() -> int:
+    return int(L.load_library().nerf_b200_launch_count())

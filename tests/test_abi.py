@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/nerf_b200.h declares; the
+host package fails loudly without CUDA (no CPU fallback).  No compute calls here."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import REPO
+
+
+def header_symbols():
+    text = open(os.path.join(REPO, "include", "nerf_b200.h")).read()
+    return sorted(set(re.findall(r"NERF_B200_API[^;]*?\b(nerf_b200_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from nerf_dbr_b200.host import lib as L
+    L.build_library()
+    import ctypes
+    so = ctypes.CDLL(L.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 16
+    for s in syms:
+        assert hasattr(so, s), f"{s} declared in include/nerf_b200.h but not exported"
+    assert sorted(L.PROTOTYPES) == syms, "ctypes prototypes out of sync with the header"
+    lib = L.load_library()
+    assert lib.nerf_b200_abi_version() == 1
+    assert lib.nerf_b200_packed_bytes() % 1024 == 0
+    assert lib.nerf_b200_error_string(-2).decode().startswith("shape not supported")
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma / tcgen05.ld / bulk-copy (TMA engine) must be in the binary (B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    from nerf_dbr_b200.host import lib as L
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    L.build_library()
+    sass = subprocess.run(["cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")      # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import ops
+    with pytest.raises(RuntimeError):
+        nb.B200Renderer()                      # same behaviour as PyTorchCUDARenderer (pytorch_renderers.py:176-178)
+    with pytest.raises(nb.NerfB200Error):
+        ops.positional_encoding(torch.zeros(4, 3), 10)
+    with pytest.raises(nb.NerfB200Error):
+        ops.composite(torch.zeros(2, 4), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(2, 3))
+
+
+def test_model_mirror_matches_reference_names(checkpoints):
+    """The host NeRFModel mirror loads reference-format state dicts and reproduces the seeded init."""
+    import nerf_dbr_b200 as nb
+    torch.manual_seed(2)
+    coarse, fine = nb.NeRFModel(), nb.NeRFModel()
+    for k, v in fine.state_dict().items():
+        assert torch.equal(v, checkpoints["rand2"]["fine_model"][k]), k
+    for k, v in coarse.state_dict().items():
+        assert torch.equal(v, checkpoints["rand2"]["coarse_model"][k]), k
+    m = nb.NeRFModel()
+    missing = m.load_state_dict(checkpoints["lego"]["fine_model"])
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert sum(p.numel() for p in m.parameters()) == 530052
