@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric: Mrays/s at 800x600, 128 samples/ray.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+
+A step = one view of the 40-view synthetic orbit (reference benchmark_suite.py:132-149) rendered
+through the fused kernel: 480,000 rays x 128 samples = 61.44 M network queries = 64.865 TFLOP
+(1,055,744 FLOP per sample, unpadded).  At N > 1 every view is cut into N
+row bands, one per GPU (strong scaling, no data-path collective); value = all rays of all ranks /
+max-over-ranks device time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, S = 800, 600, 128
+N_VIEWS = 40
+FLOP_PER_SAMPLE = 1_055_744
+METRIC = "Mrays/s at 800x600, 128 samples/ray"
+L2_FLUSH_BYTES = 256 << 20          # > 126 MB L2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def lego_weights():
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
+    return {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001 -- clocks are evidence, not a dependency
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline_sample(budget_s: float):
+    """The oracle port (torch CPU ops, the reference's algorithm and 512-ray chunks) on a bounded
+    band of view 0 of the same workload, all host threads."""
+    import torch
+    from oracle import nerf_oracle as O
+    w = lego_weights()
+    pose = O.benchmark_pose(0, N_VIEWS)
+    ro, rd = O.camera_rays(pose, W, H)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    with torch.no_grad():
+        O.render_rays(w, ro[:512], rd[:512], S)                      # warm the thread pool / allocator
+        t0 = time.perf_counter()
+        O.render_rays(w, ro[:512], rd[:512], S)
+        probe = time.perf_counter() - t0
+        chunks = max(1, min(int(budget_s / max(probe, 1e-3)), W * H // 512))
+        n = chunks * 512
+        t0 = time.perf_counter()
+        for s in range(0, n, 512):
+            O.render_rays(w, ro[s:s + 512], rd[s:s + 512], S)
+        dt = time.perf_counter() - t0
+    return n, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the path (oracle port; the reference is a
+    Python package that cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import nerf_oracle as O
+    w = lego_weights()
+    steps, warm = args.steps, args.warmup
+    per_step_budget = min(3.0, 150.0 / max(1, steps + warm))
+    poses = [O.benchmark_pose(i % N_VIEWS, N_VIEWS) for i in range(steps + warm)]
+    with torch.no_grad():
+        ro, rd = O.camera_rays(poses[0], W, H)
+        O.render_rays(w, ro.reshape(-1, 3)[:512], rd.reshape(-1, 3)[:512], S)   # warm the thread pool
+        t0 = time.perf_counter()
+        O.render_rays(w, ro.reshape(-1, 3)[:512], rd.reshape(-1, 3)[:512], S)
+        probe = time.perf_counter() - t0
+        chunks = max(1, int(per_step_budget / max(probe, 1e-3)))
+        n = min(chunks * 512, W * H)
+        times = []
+        for i, pose in enumerate(poses):
+            t0 = time.perf_counter()
+            ro, rd = O.camera_rays(pose, W, H)
+            ro, rd = ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]
+            for s in range(0, n, 512):
+                O.render_rays(w, ro[s:s + 512], rd[s:s + 512], S)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n * steps / total / 1e6
+    sample = f"first {n} rays ({n // W} rows) of each 800x600x128 view, 512-ray chunks, fine network"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "800x600x128 render, 40-view synthetic orbit (reference benchmark_suite.py:132-149)",
+                       "weights": "lego_stuffed_fp16 fixture", "sample_rays_per_step": n},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from nerf_dbr_b200.host import ops, lib as L
+    from oracle import nerf_oracle as O            # poses only (benchmark_pose restates generate_test_poses)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mode = L.BF16 if args.precision == "bf16" else L.FP32
+
+    weights = lego_weights()
+    net = ops.pack_weights({k: v.to(dev) for k, v in weights.items()}, dev)
+    # row band of this rank
+    rows = [H * r // world for r in range(world + 1)]
+    row0, n_rows = rows[rank], rows[rank + 1] - rows[rank]
+    rgb = torch.empty(n_rows, W, 3, device=dev)
+    depth = torch.empty(n_rows, W, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    poses = [O.benchmark_pose(i % N_VIEWS, N_VIEWS) for i in range(args.steps + args.warmup)]
+
+    def step(i):
+        ops.render_image(net, poses[i], W, H, S, mode, row0=row0, n_rows=n_rows, out_rgb=rgb, out_depth=depth)
+
+    # ---- device-timed: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = ops.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                                   # evicts L2 between timed steps (not timed)
+        ev[k][0].record()
+        step(args.warmup + k)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = W * H * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the public renderer API: host pose in, host image out --------------
+    import nerf_dbr_b200 as nb
+    r = nb.B200Renderer(args.precision, device_index=local)
+    r._packed = {"fine": net, "coarse": net}
+    host_rgb = torch.empty(n_rows, W, 3).pin_memory()
+    host_depth = torch.empty(n_rows, W).pin_memory()
+    host_poses = [p.pin_memory() for p in poses]
+
+    def e2e_step(i):
+        g_rgb, g_depth = r.render_rows(host_poses[i], (W, H), S, row0, n_rows, out_rgb=rgb, out_depth=depth)
+        host_rgb.copy_(g_rgb, non_blocking=True)
+        host_depth.copy_(g_depth, non_blocking=True)
+        torch.cuda.synchronize()                         # the caller holds the image
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(args.warmup + k)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = W * H * args.steps / float(t.item()) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    ms_per_launch = dev_ms / max(1, launches)            # rank 0's kernel; one launch per step
+    flops_per_launch = FLOP_PER_SAMPLE * n_rows * W * S
+    achieved = flops_per_launch / (ms_per_launch * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("fused_render_kernel_dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if mode == L.BF16 else "f32", "data": "synthetic",
+        "config": {"workload": "800x600x128 render, 40-view synthetic orbit (BASELINE.json configs[2]), "
+                               "fine network, uniform samples, image row bands sharded across GPUs",
+                   "rays_per_step": W * H, "samples_per_ray": S, "msamples_per_s": value * S,
+                   "weights": "lego_stuffed_fp16 fixture (tests/golden)", "l2": "flushed between timed steps (256 MiB memset)",
+                   "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 64,
+                "d2h_bytes_per_step": n_rows * W * 16,
+                "path": "B200Renderer.render_rows(host pose) -> pinned host rgb+depth, wall clock incl. sync"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_tflops"], "traffic": traffic,
+                     "kernel": "fused_render_kernel<SRC_POSE>", "algorithmic_flop_per_launch": flops_per_launch,
+                     "peak_source": pk["source"] + ", burst cuBLAS bf16",
+                     "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n, dt, cores = cpu_baseline_sample(12.0)
+        line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                "sample": f"first {n} rays of view 0 at 800x600x128, 512-ray chunks ({dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -220,7 +220,9 @@ __global__ void composite_kernel(const float *__restrict__ sigma, const float *_
             float zn = (s + 1 < n_samples) ? __ldg(z_vals + base + s + 1) : 0.f;
             float dist = __fmul_rn((s + 1 < n_samples) ? __fsub_rn(zn, z) : 1e10f, nrm);
             float sg = on ? fmaxf(__ldg(sigma + base + s), 0.f) : 0.f;
-            float alpha = on ? __fsub_rn(1.0f, expf(__fmul_rn(-sg, dist))) : 0.f;
+            // S == 1: the reference's `dists` is EMPTY (z[1:]-z[:-1] has no column to take [:1] from), every
+            // product broadcasts to an empty tensor and the outputs are zero -- reproduced here
+            float alpha = (on && n_samples > 1) ? __fsub_rn(1.0f, expf(__fmul_rn(-sg, dist))) : 0.f;
             float keep = on ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
             double incl = warp_incl_prod((double)keep, lane);
             double excl = __shfl_up_sync(0xffffffffu, incl, 1);

@@ -197,7 +197,7 @@ __device__ void simt_composite_ray(const float4 *__restrict__ smp, int n_samples
         }
         float4 v = on ? smp[s] : make_float4(0.f, 0.f, 0.f, 0.f);
         float dist = __fmul_rn((s + 1 < n_samples) ? __fsub_rn(zn, z) : 1e10f, dnorm);
-        float alpha = on ? __fsub_rn(1.0f, expf(__fmul_rn(-v.x, dist))) : 0.f;
+        float alpha = (on && n_samples > 1) ? __fsub_rn(1.0f, expf(__fmul_rn(-v.x, dist))) : 0.f;   // S == 1: see composite_kernel
         double keep = on ? (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -252,7 +252,7 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
     col[1] = 1.0f / (1.0f + expf(-(f0.w + f1.z + __ldg(wf + F_BC1 + 1))));
     col[2] = 1.0f / (1.0f + expf(-(f1.x + f1.w + __ldg(wf + F_BC1 + 2))));
     float alpha = 0.f, keep = 1.f, z = 0.f;
-    if (ri.valid) {
+    if (ri.valid && a.n_samples > 1) {                  // S == 1 renders black in the reference (empty dists)
         float o[3], d[3];
         ray_of<SRC>(a, ri.ray, o, d);
         float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));

@@ -210,7 +210,8 @@ SO_API void so_composite(const float *sigma, const float *rgb, const float *z_va
             float dz = (s + 1 < n_samples) ? z_vals[i + 1] - z_vals[i] : 1e10f;
             float dist = dz * nrm;
             float sg = sigma[i] > 0.0f ? sigma[i] : 0.0f;
-            float a = 1.0f - expf((-sg) * dist);
+            /* n_samples == 1: the reference's dists tensor is empty ([R,0]) and every output is 0 */
+            float a = n_samples > 1 ? 1.0f - expf((-sg) * dist) : 0.0f;
             float trans = (float)run;               /* exclusive product */
             float keep = (1.0f - a) + 1e-10f;
             run *= (double)keep;
