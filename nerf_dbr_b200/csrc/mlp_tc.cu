@@ -340,11 +340,92 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
 }
 
 // ------------------------------------------------------------------------------------------
+// epilogue of one trunk layer for one warp: 128 accumulator columns of 32 rows ->
+// + bias, ReLU, bf16, swizzled store into the next layer's A operand (2 K-blocks), with the
+// TMEM load of the next 32-column group in flight while the current one is processed.
+// kSigma (layer 7 only) also accumulates the density-head dot product from the fp32 values.
+template <bool kSigma>
+__device__ __forceinline__ float epilogue_trunk(uint32_t t_acc, int hf, uint32_t bias_addr, uint32_t wsig_addr,
+                                                uint32_t a_row, uint32_t swz, uint32_t bar_aready0, int lane)
+{
+    float sig = 0.f;
+    uint32_t v[2][32];
+    tmem_ld32(t_acc + hf * 128, v[0]);
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+        const int col0 = hf * 128 + grp * 32;
+        tmem_ld_wait();
+        if (grp < 3) tmem_ld32(t_acc + col0 + 32, v[(grp + 1) & 1]);
+        uint32_t(&x)[32] = v[grp & 1];
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = ld_shared_f4(bias_addr + (col0 + 4 * i) * 4);
+            float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
+            float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
+            add2(x0, x1, b.x, b.y);
+            add2(x2, x3, b.z, b.w);
+            pk[2 * i + 0] = relu_pack_bf16(x0, x1);
+            pk[2 * i + 1] = relu_pack_bf16(x2, x3);
+            if (kSigma) {
+                const float4 w4 = ld_shared_f4(wsig_addr + (col0 + 4 * i) * 4);
+                sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
+                sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
+            }
+        }
+        const int kb = col0 >> 6, u0 = (col0 & 63) >> 3;          // 4 x 16-byte units of K-block kb
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            st_shared_v4(a_row + kb * 16384 + (((u0 + u) ^ swz) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        if (grp & 1) {                                            // a K-block of the next A operand is complete
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready0 + 8u * kb);
+        }
+    }
+    return sig;
+}
+
+// colour layer 0 (N = 128; this warp: 64 columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
+__device__ __forceinline__ void epilogue_color(uint32_t t_acc, int hf, uint32_t rayb_addr, uint32_t wc1_addr,
+                                               float &r0, float &r1, float &r2)
+{
+    r0 = r1 = r2 = 0.f;
+    uint32_t v[2][32];
+    tmem_ld32(t_acc + hf * 64, v[0]);
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+        const int col0 = hf * 64 + grp * 32;
+        tmem_ld_wait();
+        if (grp == 0) tmem_ld32(t_acc + col0 + 32, v[1]);
+        uint32_t(&x)[32] = v[grp];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = ld_shared_f4(rayb_addr + (col0 + 4 * i) * 4);
+            const float4 w0 = ld_shared_f4(wc1_addr + (col0 + 4 * i) * 4);
+            const float4 w1 = ld_shared_f4(wc1_addr + (128 + col0 + 4 * i) * 4);
+            const float4 w2 = ld_shared_f4(wc1_addr + (256 + col0 + 4 * i) * 4);
+            float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
+            float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
+            add2(x0, x1, b.x, b.y);
+            add2(x2, x3, b.z, b.w);
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+            r0 = fmaf(x0, w0.x, r0); r0 = fmaf(x1, w0.y, r0); r0 = fmaf(x2, w0.z, r0); r0 = fmaf(x3, w0.w, r0);
+            r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
+            r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 template <int SRC>
 __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array, so the compiler keeps the
+    // shared address space (LDS/STS instead of generic LD/ST)
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_base = smem_u32(sm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bars = sm_base + SM_BAR;
@@ -439,9 +520,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         // ================================ epilogue ===========================================
         const int ew = warp - 4, q = ew & 3, hf = ew >> 2;
         const int row = q * 32 + lane;
-        const float *bias_s = reinterpret_cast<const float *>(sm + SM_BIAS);
-        const float *wsig_s = reinterpret_cast<const float *>(sm + SM_WSIG);
-        const float *wc1_s = reinterpret_cast<const float *>(sm + SM_WC1);
         const uint32_t a_row = sm_base + SM_A + row * 128;
         const uint32_t swz = (uint32_t)(row & 7);
         uint32_t g = 0;
@@ -452,71 +530,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                 wait_bar(bar(B_ACCFULL + (g & 1)), (g >> 1) & 1, a.dbg, 5);
                 tc_fence_after_sync();
                 const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256;
-                if (layer < 8) {
-                    float sig = 0.f;
-#pragma unroll 1
-                    for (int grp = 0; grp < 4; ++grp) {
-                        const int col0 = hf * 128 + grp * 32;
-                        uint32_t v[32];
-                        tmem_ld32(t_acc + col0, v);
-                        tmem_ld_wait();
-                        const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + layer * 256 + col0);
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 b = b4[i];
-                            float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                            float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                            pk[2 * i + 0] = relu_pack_bf16(x0, x1);
-                            pk[2 * i + 1] = relu_pack_bf16(x2, x3);
-                            if (layer == 7) {
-                                float4 w4 = reinterpret_cast<const float4 *>(wsig_s + col0)[i];
-                                sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
-                                sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
-                            }
-                        }
-                        const int kb = col0 >> 6, u0 = (col0 & 63) >> 3;      // 4 x 16-byte units of K-block kb
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            st_shared_v4(a_row + kb * 16384 + (((u0 + u) ^ swz) << 4),
-                                         pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                        if (grp & 1) {                                        // a K-block of the next A operand is complete
-                            tc_fence_before_sync();
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar(B_AREADY + kb));
-                        }
-                    }
-                    if (layer == 7) {
-                        if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
-                        fin[hf] = sig;
-                    }
+                if (layer < 7) {
+                    epilogue_trunk<false>(t_acc, hf, sm_base + SM_BIAS + layer * 1024, 0, a_row, swz, bar(B_AREADY), lane);
+                } else if (layer == 7) {
+                    const float sig = epilogue_trunk<true>(t_acc, hf, sm_base + SM_BIAS + 7 * 1024, sm_base + SM_WSIG,
+                                                           a_row, swz, bar(B_AREADY), lane);
+                    if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
+                    fin[hf] = sig;
                 } else {
-                    // colour layer 0 (N = 128): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
                     wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
                     const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
-                    const float *rb = reinterpret_cast<const float *>(sm + SM_RAYB) + pb * (kMaxRaysPerTile * 128) +
-                                      (row >> rpt_shift) * 128;
-                    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
-                    for (int grp = 0; grp < 2; ++grp) {
-                        const int col0 = hf * 64 + grp * 32;
-                        uint32_t v[32];
-                        tmem_ld32(t_acc + col0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 b = reinterpret_cast<const float4 *>(rb + col0)[i];
-                            float4 w0 = reinterpret_cast<const float4 *>(wc1_s + col0)[i];
-                            float4 w1 = reinterpret_cast<const float4 *>(wc1_s + 128 + col0)[i];
-                            float4 w2 = reinterpret_cast<const float4 *>(wc1_s + 256 + col0)[i];
-                            float x0 = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), x1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
-                            float x2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), x3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
-                            r0 = fmaf(x0, w0.x, r0); r0 = fmaf(x1, w0.y, r0); r0 = fmaf(x2, w0.z, r0); r0 = fmaf(x3, w0.w, r0);
-                            r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
-                            r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
-                        }
-                    }
+                    const uint32_t rayb = sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512;
+                    float r0, r1, r2;
+                    epilogue_color(t_acc, hf, rayb, sm_base + SM_WC1, r0, r1, r2);
                     fin[2 + 3 * hf + 0] = r0; fin[2 + 3 * hf + 1] = r1; fin[2 + 3 * hf + 2] = r2;
                     tc_fence_before_sync();
                     __syncwarp();

@@ -156,6 +156,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// read-only shared tables (biases, head weights): not volatile, so loads can be scheduled freely
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// (x0, x1) += (b0, b1) as one packed fp32x2 add (FADD2)
+__device__ __forceinline__ void add2(float &x0, float &x1, float b0, float b1)
+{
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
+        "add.rn.f32x2 d, a, b;\n\t"
+        "mov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(x0), "f"(x1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
