@@ -162,6 +162,9 @@ NERF_B200_API uint64_t nerf_b200_launch_count(void);
  * barrier waits are bounded: on a timeout the kernel stores 0x80000000 | code<<16 | block here and
  * traps (the launch then fails with a CUDA error instead of hanging the device). */
 NERF_B200_API void nerf_b200_set_watchdog_word(unsigned int *device_word);
+/* Optional timeline buffer (device, 6*9*8 int64, zeroed): CTA 0 of render_image(BF16) stores clock64
+ * stamps of its MMA issuer and one epilogue warp for its first 6 tiles (tools/tc_trace.py). NULL detaches. */
+NERF_B200_API void nerf_b200_set_trace_buffer(long long *device_buf);
 
 #ifdef __cplusplus
 }

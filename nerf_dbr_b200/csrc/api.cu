@@ -10,11 +10,13 @@ int tc_render_rays(const void *, const float *, const float *, int, int, float, 
 }
 using namespace nerfb200;
 
+namespace nerfb200 { extern long long *g_tc_trace; }
 static unsigned int *g_watchdog = nullptr;
 
 extern "C" {
 
 void nerf_b200_set_watchdog_word(unsigned int *device_word) { g_watchdog = device_word; }
+void nerf_b200_set_trace_buffer(long long *device_buf) { nerfb200::g_tc_trace = device_buf; }
 
 int nerf_b200_query_network(const void *packed, const float *positions, const float *directions,
                             int64_t n, int mode, float *sigma, float *rgb, void *stream)

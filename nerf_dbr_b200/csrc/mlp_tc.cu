@@ -3,16 +3,25 @@
 //   rays -> uniform/stratified depths -> positional encoding -> 8x256 MLP (+ heads) -> alpha
 //   compositing, one persistent CTA per SM, per-sample activations never leave the SM.
 //
-// Per 128-sample tile the CTA runs nine GEMMs as tcgen05.mma (M=128, N=256|128, K=16 bf16,
-// fp32 accumulators in TMEM):  L0 (K=64: encoded position), L1-L3 (K=256), L4 (K=64 encoded
-// position + K=256 hidden -- the skip is a second accumulate, not a concat), L5-L7, C0 (N=128).
-//   * A operand: activations written by the epilogue warps as bf16 into shared memory, in place,
-//     in the 128B-swizzled K-major canonical layout (4 K-blocks of [128 x 64]).
-//   * B operand: weight K-chunks ([N x 64] bf16, pre-swizzled by pack.cu) streamed L2 -> shared
-//     memory with cp.async.bulk (the TMA engine) through a 3-stage mbarrier ring.
-//   * D: two 256-column TMEM accumulators alternate per layer, so the MMA of layer l+1 starts on
-//     K-block 0 as soon as the epilogue has rewritten that K-block, while the epilogue is still
-//     reading the rest of layer l's accumulator.
+// Per 128-sample tile the CTA runs nine layers as tcgen05.mma (M=128, N=64, K=16 bf16, fp32
+// accumulators in TMEM): L0 (K=64: encoded position), L1-L3 (K=256), L4 (K=64 encoded position +
+// K=256 hidden -- the skip is a second accumulate, not a concat), L5-L7, C0 (N=128).
+//   * ACTIVATIONS LIVE IN TENSOR MEMORY.  Each layer's 256 fp32 accumulator columns are four
+//     N=64 quarters.  The epilogue reads a quarter (tcgen05.ld), adds bias, applies ReLU, packs to
+//     bf16 and writes it back IN PLACE (tcgen05.st) over the columns it has just read; the next
+//     layer's MMA takes that as its A operand straight from TMEM (no shared-memory round trip,
+//     which is what bounded the first version of this kernel: A-operand reads + epilogue stores
+//     + weight fills exceeded the 128 B/clk shared-memory port).
+//   * Two 256-column TMEM regions alternate per layer (the MMA of layer l+1 writes the other
+//     region while layer l's activations are read from this one).
+//   * MMAs are issued N-outer, quarter by quarter, so a quarter's epilogue overlaps the same
+//     layer's remaining MMAs; the chunk order (packed_layout.h) needs the previous layer's last
+//     quarter only at the 7th of 16 chunks, which hides the MMA -> epilogue -> MMA latency chain.
+//   * B operand: [64 x 64] bf16 weight chunks, pre-swizzled and stored in consumption order by
+//     pack.cu, streamed L2 -> shared memory as 32 KB cp.async.bulk stages (the TMA engine)
+//     through a 5-stage mbarrier ring.
+//   * The encoded position (bf16, 128B-swizzled K-major [128 x 64] tile) is the only A operand
+//     in shared memory (L0 and the skip part of L4).
 //   * The view direction enters colour layer 0 as an fp32 per-ray bias (W_dir . enc(d) + b),
 //     computed once per ray on CUDA cores: no per-sample direction encoding at all.
 //   * density head (256 FMAs/row) and the 128->3 colour output run in the epilogue from the fp32
@@ -20,11 +29,13 @@
 //     front/back warps, which also generate the next tile's rays, depths and encodings.
 //
 // Warp roles (512 threads): 0 weight producer | 1 MMA issuer | 2 TMEM allocator | 4-11 epilogue
-// (lane quadrant = warp % 4, column half = (warp-4)/4) | 12-15 front (encode) / back (composite).
+// (lane quadrant = warp % 4, 32-column half of a quarter = (warp-4)/4) | 12-15 front (encode) /
+// back (composite).
 //
 // reference: PyTorchCPURenderer.render_image / _render_ray_chunk (src/benchmark/
 // pytorch_renderers.py:127-170), NeRFModel.forward (src/models/nerf.py:92-131),
 // execute_volume_rendering (pytorch_renderers.py:105-125).
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -35,16 +46,13 @@ using namespace ptx;
 
 constexpr int kThreads = 512;
 constexpr int kTileM = 128;
-constexpr int kWStages = 3;
-constexpr uint32_t kWStageBytes = 32768;
-constexpr int kChunksPerTile = 34;
+constexpr int kWStages = 5;
 constexpr int kMaxRaysPerTile = 8;      // S_pad >= 16
 
 // shared memory map (bytes from a 1024-aligned base)
-constexpr uint32_t SM_A = 0;                               // 4 x [128 x 64] bf16
-constexpr uint32_t SM_PE = 65536;                          // 2 x [128 x 64] bf16
-constexpr uint32_t SM_W = 98304;                           // kWStages x 32 KB
-constexpr uint32_t SM_BIAS = SM_W + kWStages * kWStageBytes;   // [8][256] f32
+constexpr uint32_t SM_PE = 0;                              // 2 x [128 x 64] bf16 encoded-position tiles
+constexpr uint32_t SM_W = 32768;                           // kWStages x 32 KB weight stages
+constexpr uint32_t SM_BIAS = SM_W + kWStages * kStageBytes;    // [8][256] f32
 constexpr uint32_t SM_WSIG = SM_BIAS + 8192;               // [256] f32
 constexpr uint32_t SM_WC1 = SM_WSIG + 1024;                // [3][128] f32
 constexpr uint32_t SM_RAYB = SM_WC1 + 1536;                // [2][8][128] f32  per-ray colour-0 bias
@@ -58,27 +66,12 @@ constexpr uint32_t kSmemBytes = SM_TOTAL + 1024;           // + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 3, B_PEFULL = 6, B_PEEMPTY = 8, B_AREADY = 10, B_ACCFULL = 14,
-       B_FINFULL = 16, B_FINEMPTY = 18, B_COUNT = 20 };
+enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kWStages, B_PEFULL = B_WEMPTY + kWStages, B_PEEMPTY = B_PEFULL + 2,
+       B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 4, B_FINFULL = B_AREADY + 4, B_FINEMPTY = B_FINFULL + 2,
+       B_COUNT = B_FINEMPTY + 2 };
+static_assert(B_COUNT * 8 <= 256, "barrier area");
 
-// chunk consumption order per tile: index into the packed chunk stream (packed_layout.h).
-// K-blocks of a layer are consumed 0,2,1,3 (both column halves of the previous epilogue finish
-// their first K-block at the same time); layer 4 takes its encoded-position chunk first, because
-// that operand does not wait for the previous epilogue.
-__constant__ uint8_t kOrder[kChunksPerTile] = {
-    0,                 // L0
-    1, 3, 2, 4,        // L1
-    5, 7, 6, 8,        // L2
-    9, 11, 10, 12,     // L3
-    17, 13, 15, 14, 16,// L4 (pe, h0, h2, h1, h3)
-    18, 20, 19, 21,    // L5
-    22, 24, 23, 25,    // L6
-    26, 28, 27, 29,    // L7
-    30, 32, 31, 33};   // C0
-// which A K-block a chunk multiplies: 0..3 = hidden K-block, 4 = encoded-position tile
-__constant__ uint8_t kASrc[kChunksPerTile] = {
-    4, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 4, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3, 0, 2, 1, 3};
-__constant__ uint8_t kLayerChunks[9] = {1, 4, 4, 4, 5, 4, 4, 4, 4};
+__constant__ ChunkTable kChunks = make_chunk_table();
 
 enum { SRC_RAYS = 1, SRC_POSE = 2 };
 
@@ -95,7 +88,14 @@ struct Args {
     float near, far;
     float *rgb_map, *depth, *acc;
     unsigned int *dbg;         // optional: [0] = first timeout code
+    long long *trace;          // optional timeline (tools/tc_trace.py): CTA 0, first kTraceTiles tiles
 };
+constexpr int kTraceTiles = 6;
+// trace layout: [tile][layer 0..8][slot 0..7] clock64 stamps
+//   0 MMA: first chunk of the layer issued   1 MMA: quarter 0 committed   2 MMA: last quarter committed
+//   3 EPI(warp 4): quarter 0 acc_full seen   4 EPI: quarter 0 a_ready arrive   5 EPI: last quarter done
+//   6 MMA: stalled cycles waiting for a_ready in this layer   7 MMA: stalled cycles waiting for w_full
+#define TC_TRACE(tile, layer, slot) do { if (a.trace && blockIdx.x == 0 && (tile) < kTraceTiles) a.trace[((tile) * 9 + (layer)) * 8 + (slot)] = clock64(); } while (0)
 
 constexpr long long kTimeoutCycles = 4000000000LL;
 
@@ -340,81 +340,56 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue of one trunk layer for one warp: 128 accumulator columns of 32 rows ->
-// + bias, ReLU, bf16, swizzled store into the next layer's A operand (2 K-blocks), with the
-// TMEM load of the next 32-column group in flight while the current one is processed.
+// epilogue of one N=64 accumulator quarter for one warp (32 rows x 32 columns): tcgen05.ld,
+// + bias, ReLU, bf16, and tcgen05.st of the 16 packed columns back over the first half of the
+// columns this warp has just read (the next layer's A operand, K-major in TMEM).
 // kSigma (layer 7 only) also accumulates the density-head dot product from the fp32 values.
 template <bool kSigma>
-__device__ __forceinline__ float epilogue_trunk(uint32_t t_acc, int hf, uint32_t bias_addr, uint32_t wsig_addr,
-                                                uint32_t a_row, uint32_t swz, uint32_t bar_aready0, int lane)
+__device__ __forceinline__ void epilogue_quarter(uint32_t t_cols, uint32_t bias_addr, uint32_t wsig_addr, float &sig)
 {
-    float sig = 0.f;
-    uint32_t v[2][32];
-    tmem_ld32(t_acc + hf * 128, v[0]);
+    uint32_t x[32], pk[16];
+    tmem_ld32(t_cols, x);
+    tmem_ld_wait();
 #pragma unroll
-    for (int grp = 0; grp < 4; ++grp) {
-        const int col0 = hf * 128 + grp * 32;
-        tmem_ld_wait();
-        if (grp < 3) tmem_ld32(t_acc + col0 + 32, v[(grp + 1) & 1]);
-        uint32_t(&x)[32] = v[grp & 1];
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = ld_shared_f4(bias_addr + (col0 + 4 * i) * 4);
-            float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
-            float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
-            add2(x0, x1, b.x, b.y);
-            add2(x2, x3, b.z, b.w);
-            pk[2 * i + 0] = relu_pack_bf16(x0, x1);
-            pk[2 * i + 1] = relu_pack_bf16(x2, x3);
-            if (kSigma) {
-                const float4 w4 = ld_shared_f4(wsig_addr + (col0 + 4 * i) * 4);
-                sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
-                sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
-            }
-        }
-        const int kb = col0 >> 6, u0 = (col0 & 63) >> 3;          // 4 x 16-byte units of K-block kb
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            st_shared_v4(a_row + kb * 16384 + (((u0 + u) ^ swz) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        if (grp & 1) {                                            // a K-block of the next A operand is complete
-            tc_fence_before_sync();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready0 + 8u * kb);
+    for (int i = 0; i < 8; ++i) {
+        const float4 b = ld_shared_f4(bias_addr + 16 * i);
+        float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
+        float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
+        add2(x0, x1, b.x, b.y);
+        add2(x2, x3, b.z, b.w);
+        pk[2 * i + 0] = relu_pack_bf16(x0, x1);
+        pk[2 * i + 1] = relu_pack_bf16(x2, x3);
+        if (kSigma) {
+            const float4 w4 = ld_shared_f4(wsig_addr + 16 * i);
+            sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
+            sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
         }
     }
-    return sig;
+    tmem_st16(t_cols, pk);
+    tmem_st_wait();
 }
 
-// colour layer 0 (N = 128; this warp: 64 columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
-__device__ __forceinline__ void epilogue_color(uint32_t t_acc, int hf, uint32_t rayb_addr, uint32_t wc1_addr,
-                                               float &r0, float &r1, float &r2)
+// colour layer 0, one quarter (32 of this warp's columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
+__device__ __forceinline__ void epilogue_color_quarter(uint32_t t_cols, uint32_t rayb_addr, uint32_t wc1_addr,
+                                                       float &r0, float &r1, float &r2)
 {
-    r0 = r1 = r2 = 0.f;
-    uint32_t v[2][32];
-    tmem_ld32(t_acc + hf * 64, v[0]);
+    uint32_t x[32];
+    tmem_ld32(t_cols, x);
+    tmem_ld_wait();
 #pragma unroll
-    for (int grp = 0; grp < 2; ++grp) {
-        const int col0 = hf * 64 + grp * 32;
-        tmem_ld_wait();
-        if (grp == 0) tmem_ld32(t_acc + col0 + 32, v[1]);
-        uint32_t(&x)[32] = v[grp];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = ld_shared_f4(rayb_addr + (col0 + 4 * i) * 4);
-            const float4 w0 = ld_shared_f4(wc1_addr + (col0 + 4 * i) * 4);
-            const float4 w1 = ld_shared_f4(wc1_addr + (128 + col0 + 4 * i) * 4);
-            const float4 w2 = ld_shared_f4(wc1_addr + (256 + col0 + 4 * i) * 4);
-            float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
-            float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
-            add2(x0, x1, b.x, b.y);
-            add2(x2, x3, b.z, b.w);
-            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-            r0 = fmaf(x0, w0.x, r0); r0 = fmaf(x1, w0.y, r0); r0 = fmaf(x2, w0.z, r0); r0 = fmaf(x3, w0.w, r0);
-            r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
-            r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
-        }
+    for (int i = 0; i < 8; ++i) {
+        const float4 b = ld_shared_f4(rayb_addr + 16 * i);
+        const float4 w0 = ld_shared_f4(wc1_addr + 16 * i);
+        const float4 w1 = ld_shared_f4(wc1_addr + 512 + 16 * i);
+        const float4 w2 = ld_shared_f4(wc1_addr + 1024 + 16 * i);
+        float x0 = __uint_as_float(x[4 * i + 0]), x1 = __uint_as_float(x[4 * i + 1]);
+        float x2 = __uint_as_float(x[4 * i + 2]), x3 = __uint_as_float(x[4 * i + 3]);
+        add2(x0, x1, b.x, b.y);
+        add2(x2, x3, b.z, b.w);
+        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        r0 = fmaf(x0, w0.x, r0); r0 = fmaf(x1, w0.y, r0); r0 = fmaf(x2, w0.z, r0); r0 = fmaf(x3, w0.w, r0);
+        r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
+        r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
     }
 }
 
@@ -442,10 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         for (int i = 0; i < kWStages; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
-            mbar_init(bar(B_ACCFULL + i), 1);
             mbar_init(bar(B_FINFULL + i), 8); mbar_init(bar(B_FINEMPTY + i), 4);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), 4);
+        for (int i = 0; i < 4; ++i) { mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_AREADY + i), 8); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(sm_base + SM_TMEM);
@@ -464,90 +438,137 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 
     if (warp == 0) {
         // ================================ weight producer ===================================
+        // the packed stream is already in consumption order: 32 consecutive 32 KB stages per tile
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t sg = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                for (int c = 0; c < kChunksPerTile; ++c, ++it) {
-                    const uint32_t stage = it % kWStages, round = it / kWStages;
-                    if (round > 0) wait_bar(bar(B_WEMPTY + stage), (round - 1) & 1, a.dbg, 1);
-                    const int ci = kOrder[c];
-                    const uint32_t bytes = ci < kChunks256 ? (uint32_t)kChunkBytes256 : (uint32_t)kChunkBytes128;
-                    const unsigned char *src = ci < kChunks256 ? wb + (size_t)ci * kChunkBytes256
-                                                               : wb + B_C0 + (size_t)(ci - kChunks256) * kChunkBytes128;
-                    mbar_arrive_expect_tx(bar(B_WFULL + stage), bytes);
-                    bulk_g2s(sm_base + SM_W + stage * kWStageBytes, src, bytes, bar(B_WFULL + stage));
+                for (int st = 0; st < kStagesPerTile; ++st, ++sg) {
+                    const uint32_t slot = sg % kWStages, round = sg / kWStages;
+                    if (round > 0) wait_bar(bar(B_WEMPTY + slot), (round - 1) & 1, a.dbg, 1);
+                    mbar_arrive_expect_tx(bar(B_WFULL + slot), kStageBytes);
+                    bulk_g2s(sm_base + SM_W + slot * kStageBytes, wb + (size_t)st * kStageBytes, kStageBytes,
+                             bar(B_WFULL + slot));
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer =========================================
         if (lane == 0) {
-            uint32_t it = 0, g = 0, a_uses = 0;     // a_uses: completed uses of each a_ready barrier
-            const uint32_t idesc256 = idesc_bf16(128, 256), idesc128 = idesc_bf16(128, 128);
+            uint32_t sg = 0, g = 0;
+            const uint32_t idesc = idesc_bf16(128, 64);
             for (int t = 0; t < my_tiles; ++t) {
                 const int pb = t & 1;
                 wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 2);
-                int c = 0;
-                for (int layer = 0; layer < 9; ++layer, ++g) {
-                    const uint32_t d_tmem = tmem_base + (g & 1) * 256;
-                    const uint32_t idesc = layer == 8 ? idesc128 : idesc256;
-                    const int nch = kLayerChunks[layer];
-                    for (int j = 0; j < nch; ++j, ++c, ++it) {
-                        const int asrc = kASrc[c];
-                        uint32_t a_addr;
-                        if (asrc == 4) a_addr = sm_base + SM_PE + pb * 16384;
-                        else {
-                            a_addr = sm_base + SM_A + asrc * 16384;
-                            wait_bar(bar(B_AREADY + asrc), a_uses & 1, a.dbg, 3);
-                        }
-                        const uint32_t stage = it % kWStages;
-                        wait_bar(bar(B_WFULL + stage), (it / kWStages) & 1, a.dbg, 4);
-                        tc_fence_after_sync();
-                        const uint64_t adesc = smem_desc_sw128(a_addr);
-                        const uint64_t bdesc = smem_desc_sw128(sm_base + SM_W + stage * kWStageBytes);
+                uint32_t kb_seen = 0;               // a_ready[kb] already waited for in this layer
+                int cur_layer = 0;
+                long long stall_a = 0, stall_w = 0;
+                for (int ci = 0; ci < kChunksPerTile; ++ci) {
+                    const ChunkInfo c = kChunks.c[ci];
+                    if (c.layer != cur_layer) {
+                        cur_layer = c.layer; kb_seen = 0; ++g;
+                        stall_a = stall_w = 0;
+                    }
+                    const uint32_t slot = sg % kWStages;
+                    if ((ci & 3) == 0) {
+                        const long long t0 = a.trace ? clock64() : 0;
+                        wait_bar(bar(B_WFULL + slot), (sg / kWStages) & 1, a.dbg, 4);
+                        if (a.trace) stall_w += clock64() - t0;
+                    }
+                    if (c.asrc < 4 && !(kb_seen & (1u << c.asrc))) {
+                        const long long t0 = a.trace ? clock64() : 0;
+                        // a_ready[kb] completes once per producing layer (0..7: 8 phases per tile, so the parity
+                        // restarts every tile); layer l consumes the phase produced by layer l-1
+                        wait_bar(bar(B_AREADY + c.asrc), (c.layer - 1) & 1, a.dbg, 3);
+                        if (a.trace) stall_a += clock64() - t0;
+                        kb_seen |= 1u << c.asrc;
+                    }
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + (g & 1) * 256 + c.nq * 64;
+                    const uint64_t bdesc = smem_desc_sw128(sm_base + SM_W + slot * kStageBytes + (ci & 3) * kChunkBytes);
+                    if (c.asrc == 4) {
+                        const uint64_t adesc = smem_desc_sw128(sm_base + SM_PE + pb * 16384);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)      // 4 x (K = 16): +32 B inside the 128 B swizzle span
-                            mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | k) != 0);
-                        mma_commit(bar(B_WEMPTY + stage));
+                            mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
+                    } else {
+                        // A = previous layer's quarter `asrc`, bf16 in place in the other TMEM region:
+                        // K 0..31 in columns +0..15 (written by the half-0 warps), K 32..63 in columns +32..47
+                        const uint32_t a_tmem = tmem_base + ((g & 1) ^ 1) * 256 + c.asrc * 64;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16_ts(d_tmem, a_tmem + (k >> 1) * 32 + (k & 1) * 8, bdesc + 2 * k, idesc,
+                                        !((c.flags & 1) && k == 0));
                     }
-                    mma_commit(bar(B_ACCFULL + (g & 1)));
-                    if (layer == 4) mma_commit(bar(B_PEEMPTY + pb));
-                    if (layer >= 1) ++a_uses;         // layers 1..8 consumed one phase of every a_ready[kb]
+                    if (c.flags & 1) { if (c.nq == 0) TC_TRACE(t, c.layer, 0); }
+                    if (c.flags & 2) {
+                        mma_commit(bar(B_ACCFULL + c.nq));
+                        if (c.nq == 0) TC_TRACE(t, c.layer, 1);
+                        if (c.nq == (c.layer == 8 ? 1 : 3)) {
+                            TC_TRACE(t, c.layer, 2);
+                            if (a.trace && blockIdx.x == 0 && t < kTraceTiles) {
+                                a.trace[(t * 9 + c.layer) * 8 + 6] = stall_a;
+                                a.trace[(t * 9 + c.layer) * 8 + 7] = stall_w;
+                            }
+                        }
+                    }
+                    if ((ci & 3) == 3) { mma_commit(bar(B_WEMPTY + slot)); ++sg; }
+                    if (c.layer == 4 && (c.flags & 2) && c.nq == 3) mma_commit(bar(B_PEEMPTY + pb));
                 }
+                ++g;                                // next tile's layer 0
             }
         }
     } else if (warp >= 4 && warp < 12) {
         // ================================ epilogue ===========================================
-        const int ew = warp - 4, q = ew & 3, hf = ew >> 2;
+        const int ew = warp - 4, q = ew & 3, h = ew >> 2;
         const int row = q * 32 + lane;
-        const uint32_t a_row = sm_base + SM_A + row * 128;
-        const uint32_t swz = (uint32_t)(row & 7);
-        uint32_t g = 0;
+        uint32_t g = 0, acc_uses[4] = {0, 0, 0, 0};
         for (int t = 0; t < my_tiles; ++t) {
             const int pb = t & 1, fb = t & 1;
             float *fin = reinterpret_cast<float *>(sm + SM_FIN + fb * 4096 + row * 32);
             for (int layer = 0; layer < 9; ++layer, ++g) {
-                wait_bar(bar(B_ACCFULL + (g & 1)), (g >> 1) & 1, a.dbg, 5);
-                tc_fence_after_sync();
-                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256;
-                if (layer < 7) {
-                    epilogue_trunk<false>(t_acc, hf, sm_base + SM_BIAS + layer * 1024, 0, a_row, swz, bar(B_AREADY), lane);
-                } else if (layer == 7) {
-                    const float sig = epilogue_trunk<true>(t_acc, hf, sm_base + SM_BIAS + 7 * 1024, sm_base + SM_WSIG,
-                                                           a_row, swz, bar(B_AREADY), lane);
-                    if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
-                    fin[hf] = sig;
+                const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 32 * h;
+                if (layer < 8) {
+                    float sig = 0.f;
+#pragma unroll
+                    for (int nq = 0; nq < 4; ++nq) {
+                        wait_bar(bar(B_ACCFULL + nq), acc_uses[nq] & 1, a.dbg, 5);
+                        ++acc_uses[nq];
+                        tc_fence_after_sync();
+                        if (nq == 0 && ew == 0 && lane == 0) TC_TRACE(t, layer, 3);
+                        const uint32_t col = layer * 256 + nq * 64 + 32 * h;
+                        if (layer == 7)
+                            epilogue_quarter<true>(t_lane + nq * 64, sm_base + SM_BIAS + col * 4,
+                                                   sm_base + SM_WSIG + (nq * 64 + 32 * h) * 4, sig);
+                        else
+                            epilogue_quarter<false>(t_lane + nq * 64, sm_base + SM_BIAS + col * 4, 0, sig);
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(B_AREADY + nq));
+                        if (nq == 0 && ew == 0 && lane == 0) TC_TRACE(t, layer, 4);
+                    }
+                    if (layer == 7) {
+                        if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
+                        fin[h] = sig;
+                    }
                 } else {
                     wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
                     const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
                     const uint32_t rayb = sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512;
-                    float r0, r1, r2;
-                    epilogue_color(t_acc, hf, rayb, sm_base + SM_WC1, r0, r1, r2);
-                    fin[2 + 3 * hf + 0] = r0; fin[2 + 3 * hf + 1] = r1; fin[2 + 3 * hf + 2] = r2;
+                    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+                    for (int nq = 0; nq < 2; ++nq) {
+                        wait_bar(bar(B_ACCFULL + nq), acc_uses[nq] & 1, a.dbg, 5);
+                        ++acc_uses[nq];
+                        tc_fence_after_sync();
+                        const uint32_t n0 = nq * 64 + 32 * h;
+                        epilogue_color_quarter(t_lane + nq * 64, rayb + n0 * 4, sm_base + SM_WC1 + n0 * 4, r0, r1, r2);
+                    }
+                    fin[2 + 3 * h + 0] = r0; fin[2 + 3 * h + 1] = r1; fin[2 + 3 * h + 2] = r2;
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(B_FINFULL + fb));
                 }
+                if (ew == 0 && lane == 0) TC_TRACE(t, layer, 5);
             }
         }
     } else if (warp >= 12) {
@@ -618,11 +639,14 @@ static int launch(Args &a, cudaStream_t stream)
 
 }  // namespace tc
 
+long long *g_tc_trace = nullptr;     // set through nerf_b200_set_trace_buffer (tools/tc_trace.py)
+
 int tc_render_pose(const void *packed, const float *c2w, int width, int height, float focal, float near,
                    float far, int n_samples, int row0, int n_rows, float *rgb_out, float *depth_out,
                    unsigned int *dbg, cudaStream_t stream)
 {
     tc::Args a = {};
+    a.trace = g_tc_trace;
     a.packed = reinterpret_cast<const unsigned char *>(packed);
     a.pose = pose_from_c2w(c2w);
     a.width = width; a.row0 = row0;

@@ -4,17 +4,20 @@
 
 namespace nerfb200 {
 
-struct ChunkSrc { const float *w; int ld; int k0; int k_valid; };   // rows n, columns k0..k0+63
+struct ChunkSrc { const float *w; int ld; int n0; int k0; int k_valid; };   // rows n0.., columns k0..k0+63
 
-// source of bf16 chunk `ci` (0..29: N=256 chunks, 30..33: colour-0 N=128 chunks)
+__constant__ ChunkTable kPackTable = make_chunk_table();
+
+// source of bf16 chunk `ci` of the consumption-ordered stream (packed_layout.h)
 __device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int ci)
 {
-    if (ci == 0) return {p.layer_w[0], 63, 0, 63};
-    if (ci <= 12) { int l = 1 + (ci - 1) / 4, kc = (ci - 1) % 4; return {p.layer_w[l], 256, kc * 64, 64}; }
-    if (ci <= 16) return {p.layer_w[4], 319, (ci - 13) * 64, 64};
-    if (ci == 17) return {p.layer_w[4], 319, 256, 63};
-    if (ci <= 29) { int l = 5 + (ci - 18) / 4, kc = (ci - 18) % 4; return {p.layer_w[l], 256, kc * 64, 64}; }
-    return {p.color0_w, 283, (ci - 30) * 64, 64};
+    const ChunkInfo c = kPackTable.c[ci];
+    const int n0 = 64 * c.nq;
+    if (c.layer == 0) return {p.layer_w[0], 63, n0, 0, 63};
+    if (c.layer == 8) return {p.color0_w, 283, n0, 64 * c.asrc, 64};
+    if (c.layer == 4) return c.asrc == 4 ? ChunkSrc{p.layer_w[4], 319, n0, 256, 63}
+                                         : ChunkSrc{p.layer_w[4], 319, n0, 64 * c.asrc, 64};
+    return {p.layer_w[c.layer], 256, n0, 64 * c.asrc, 64};
 }
 
 __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ packed)
@@ -45,21 +48,19 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
     }
 
     // ---- bf16 region: one 16-byte unit (8 consecutive k of one row) per thread-iteration ----
-    const size_t units256 = (size_t)kChunks256 * 256 * 8, units = units256 + (size_t)kChunks128 * 128 * 8;
+    const size_t units = (size_t)kChunksPerTile * 64 * 8;
     for (size_t uidx = tid; uidx < units; uidx += nth) {
-        int ci, n, unit; size_t chunk_off;
-        if (uidx < units256) { ci = (int)(uidx / 2048); n = (int)((uidx % 2048) / 8); unit = (int)(uidx % 8); chunk_off = (size_t)ci * kChunkBytes256; }
-        else { size_t r = uidx - units256; ci = 30 + (int)(r / 1024); n = (int)((r % 1024) / 8); unit = (int)(r % 8); chunk_off = B_C0 + (size_t)(ci - 30) * kChunkBytes128; }
-        ChunkSrc src = chunk_source(p, ci);
+        const int ci = (int)(uidx / 512), n = (int)((uidx % 512) / 8), unit = (int)(uidx % 8);
+        const ChunkSrc src = chunk_source(p, ci);
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int k = unit * 8 + j;
-            float w = k < src.k_valid ? src.w[(size_t)n * src.ld + src.k0 + k] : 0.f;
+            float w = k < src.k_valid ? src.w[(size_t)(src.n0 + n) * src.ld + src.k0 + k] : 0.f;
             hi[j] = __float2bfloat16_rn(w);
             lo[j] = __float2bfloat16_rn(w - __bfloat162float(hi[j]));
         }
-        size_t off = chunk_off + swz128((uint32_t)n, (uint32_t)unit * 8);
+        size_t off = (size_t)ci * kChunkBytes + swz128((uint32_t)n, (uint32_t)unit * 8);
         *reinterpret_cast<uint4 *>(packed + B_OFFSET + off) = *reinterpret_cast<const uint4 *>(hi);
         *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
     }

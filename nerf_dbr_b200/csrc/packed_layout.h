@@ -37,16 +37,68 @@ constexpr size_t F_END = F_WC0D + 32 * 128;
 __host__ __device__ constexpr size_t f_wt(int layer) { return F_WT + (size_t)(layer - 1) * 256 * 256; }
 
 // ---- bf16 region --------------------------------------------------------------------------
-constexpr size_t kChunkBytes256 = 256 * 128;                  // [256 x 64] bf16
-constexpr size_t kChunkBytes128 = 128 * 128;                  // [128 x 64] bf16
-// chunk sequence per sample tile: L0 (1: pe) | L1..L3 (4 each) | L4 (4 hidden + 1 pe) |
-// L5..L7 (4 each) | C0 (4 chunks of N=128)
-constexpr int kChunks256 = 1 + 12 + 5 + 12;                   // 30
-constexpr int kChunks128 = 4;
+// The tcgen05 kernel computes every layer as N = 64 output-column quarters (4 per 256-wide layer,
+// 2 for colour layer 0) and streams the weights as [64 n x 64 k] bf16 chunks (8 KB, 128B-swizzled
+// K-major) in EXACTLY the order its MMA issuer consumes them, so the producer warp just copies
+// consecutive 32 KB stages (4 chunks).  Per 128-sample tile: 128 chunks = 32 stages = 1 MiB.
+//
+// Order inside a layer ("N-outer, last K-block late"): quarters 0 and 1 first take K-blocks
+// 0,1,2 (and the encoded-position chunk, layer 4), then K-block 3 of both, then quarters 2 and 3
+// in plain order.  Quarter accumulators therefore complete one after another (their epilogues
+// overlap the layer's remaining MMAs) and the previous layer's LAST quarter -- whose epilogue
+// finishes last -- is not needed before the 7th chunk.
+constexpr int kChunkBytes = 64 * 128;                         // [64 x 64] bf16
+constexpr int kChunksPerTile = 128;
+constexpr int kStageChunks = 4;
+constexpr int kStageBytes = kStageChunks * kChunkBytes;       // 32 KB
+constexpr int kStagesPerTile = kChunksPerTile / kStageChunks; // 32
+
+struct ChunkInfo {
+    uint8_t layer;   // 0..7 trunk, 8 = colour layer 0
+    uint8_t nq;      // output quarter: columns [64 nq, 64 nq + 64)
+    uint8_t asrc;    // A operand: 0..3 = hidden K-block (previous layer's quarter), 4 = encoded position
+    uint8_t flags;   // 1 = first chunk of this quarter (overwrite), 2 = last chunk of this quarter
+};
+struct ChunkTable { ChunkInfo c[kChunksPerTile]; };
+
+constexpr ChunkTable make_chunk_table()
+{
+    ChunkTable t{};
+    int n = 0;
+    for (int layer = 0; layer < 9; ++layer) {
+        const int quarters = layer == 8 ? 2 : 4;
+        const bool pe = layer == 4;
+        const int begin = n;
+        if (layer == 0) {
+            for (int q = 0; q < 4; ++q) t.c[n++] = ChunkInfo{0, (uint8_t)q, 4, 3};
+            continue;
+        }
+        for (int q = 0; q < 2; ++q) {
+            if (pe) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, 4, 0};
+            for (int kb = 0; kb < 3; ++kb) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, (uint8_t)kb, 0};
+        }
+        t.c[n++] = ChunkInfo{(uint8_t)layer, 0, 3, 0};
+        t.c[n++] = ChunkInfo{(uint8_t)layer, 1, 3, 0};
+        for (int q = 2; q < quarters; ++q) {
+            if (pe) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, 4, 0};
+            for (int kb = 0; kb < 4; ++kb) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, (uint8_t)kb, 0};
+        }
+        // first / last chunk of every quarter of this layer
+        for (int q = 0; q < quarters; ++q) {
+            int first = -1, last = -1;
+            for (int i = begin; i < n; ++i)
+                if (t.c[i].nq == q) { if (first < 0) first = i; last = i; }
+            t.c[first].flags |= 1;
+            t.c[last].flags |= 2;
+        }
+    }
+    return t;
+}
+static_assert(make_chunk_table().c[kChunksPerTile - 1].layer == 8, "chunk table must fill exactly 128 entries");
+
 constexpr size_t B_OFFSET = ((F_END * 4 + 1023) / 1024) * 1024;   // byte offset of the bf16 region
-constexpr size_t B_C0 = (size_t)kChunks256 * kChunkBytes256;      // byte offset of colour-0 chunks inside it
-constexpr size_t B_BYTES = B_C0 + (size_t)kChunks128 * kChunkBytes128;
-// optional low-order bf16 stream for the split-precision mode follows (same layout)
+constexpr size_t B_BYTES = (size_t)kChunksPerTile * kChunkBytes;  // 1 MiB
+// low-order bf16 stream for a split-precision mode follows (same layout)
 constexpr size_t B_LO_OFFSET = B_OFFSET + B_BYTES;
 constexpr size_t PACKED_BYTES = B_LO_OFFSET + B_BYTES;
 

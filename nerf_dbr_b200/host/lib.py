@@ -59,6 +59,7 @@ PROTOTYPES = {
                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_launch_count": (c_uint64, []),
     "nerf_b200_set_watchdog_word": (None, [c_void_p]),
+    "nerf_b200_set_trace_buffer": (None, [c_void_p]),
 }
 
 

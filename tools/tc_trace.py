@@ -1,0 +1,30 @@
+"""Per-layer timeline of the tensor-core kernel (CTA 0, first tiles).  Run under gpurun."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from nerf_dbr_b200.host import ops, lib as L
+from oracle import nerf_oracle as O
+
+dev = torch.device("cuda", 0)
+z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
+net = ops.pack_weights({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev)
+pose = O.benchmark_pose(1, 40)
+ops.render_image(net, pose, 800, 600, 128, mode=1)
+torch.cuda.synchronize()
+buf = torch.zeros(6 * 9 * 8, dtype=torch.int64, device=dev)
+L.load_library().nerf_b200_set_trace_buffer(ctypes.c_void_p(buf.data_ptr()))
+ops.render_image(net, pose, 800, 600, 128, mode=1)
+torch.cuda.synchronize()
+L.load_library().nerf_b200_set_trace_buffer(None)
+t = buf.cpu().numpy().reshape(6, 9, 8)
+t0 = t[:, :, :6][t[:, :, :6] > 0].min()
+print("tile layer  mma_first  q0_commit last_commit  epi_q0_acc epi_q0_arr  epi_done | stall_a stall_w | layer_period q0commit->acc acc->arrive")
+for ti in range(2, 6):
+    for l in range(9):
+        r = t[ti, l].astype(np.int64)
+        rel = r[:6] - t0
+        nxt = t[ti, l + 1, 0] if l < 8 else (t[ti + 1, 0, 0] if ti + 1 < 6 else 0)
+        print(f"{ti:4d} {l:5d} " + " ".join(f"{int(v):10d}" for v in rel) + f" | {int(r[6]):7d} {int(r[7]):7d} | "
+              f"{int(nxt - r[0]) if nxt else -1:8d} {int(r[3]-r[1]):10d} {int(r[4]-r[3]):10d}")
+print("tile period (cycles):", (t[5, 0, 0] - t[2, 0, 0]) / 3)
