@@ -3,23 +3,27 @@
 //   rays -> uniform/stratified depths -> positional encoding -> 8x256 MLP (+ heads) -> alpha
 //   compositing, one persistent CTA per SM, per-sample activations never leave the SM.
 //
-// Per 128-sample tile the CTA runs nine layers as tcgen05.mma (M=128, N=64, K=16 bf16, fp32
+// Per 128-sample tile the CTA runs nine layers as tcgen05.mma (M=128, N=128, K=16 bf16, fp32
 // accumulators in TMEM): L0 (K=64: encoded position), L1-L3 (K=256), L4 (K=64 encoded position +
 // K=256 hidden -- the skip is a second accumulate, not a concat), L5-L7, C0 (N=128).
-//   * ACTIVATIONS LIVE IN TENSOR MEMORY.  Each layer's 256 fp32 accumulator columns are four
-//     N=64 quarters.  The epilogue reads a quarter (tcgen05.ld), adds bias, applies ReLU, packs to
+//   * ACTIVATIONS LIVE IN TENSOR MEMORY.  Each layer's 256 fp32 accumulator columns are two
+//     N=128 halves.  The epilogue reads a half (tcgen05.ld), adds bias, applies ReLU, packs to
 //     bf16 and writes it back IN PLACE (tcgen05.st) over the columns it has just read; the next
 //     layer's MMA takes that as its A operand straight from TMEM (no shared-memory round trip,
 //     which is what bounded the first version of this kernel: A-operand reads + epilogue stores
 //     + weight fills exceeded the 128 B/clk shared-memory port).
 //   * Two 256-column TMEM regions alternate per layer (the MMA of layer l+1 writes the other
 //     region while layer l's activations are read from this one).
-//   * MMAs are issued N-outer, quarter by quarter, so a quarter's epilogue overlaps the same
-//     layer's remaining MMAs; the chunk order (packed_layout.h) needs the previous layer's last
-//     quarter only at the 7th of 16 chunks, which hides the MMA -> epilogue -> MMA latency chain.
-//   * B operand: [64 x 64] bf16 weight chunks, pre-swizzled and stored in consumption order by
+//   * The chunk order (packed_layout.h: h0k0 h0k1 h1k0 h0k2 h0k3 h1k1 h1k2 h1k3) lets half 0's
+//     epilogue overlap the same layer's remaining MMAs and half 1's the next layer's first three
+//     chunks, which hides the MMA -> epilogue -> MMA latency chain (~750 cycles of slack).
+//   * The MMA issuer is straight-line code: the whole per-tile schedule (64 chunks, 256 MMAs) is
+//     unrolled at compile time from the constexpr chunk table, every barrier parity, ring slot and
+//     operand offset an immediate -- a table-driven loop issues ~1 MMA per 190 cycles, this one
+//     keeps up with the pipe's 64 cycles per instruction.
+//   * B operand: [128 x 64] bf16 weight chunks, pre-swizzled and stored in consumption order by
 //     pack.cu, streamed L2 -> shared memory as 32 KB cp.async.bulk stages (the TMA engine)
-//     through a 5-stage mbarrier ring.
+//     through a 4-stage mbarrier ring.
 //   * The encoded position (bf16, 128B-swizzled K-major [128 x 64] tile) is the only A operand
 //     in shared memory (L0 and the skip part of L4).
 //   * The view direction enters colour layer 0 as an fp32 per-ray bias (W_dir . enc(d) + b),
@@ -29,13 +33,14 @@
 //     front/back warps, which also generate the next tile's rays, depths and encodings.
 //
 // Warp roles (512 threads): 0 weight producer | 1 MMA issuer | 2 TMEM allocator | 4-11 epilogue
-// (lane quadrant = warp % 4, 32-column half of a quarter = (warp-4)/4) | 12-15 front (encode) /
+// (lane quadrant = warp % 4, 64-column part of a half = (warp-4)/4) | 12-15 front (encode) /
 // back (composite).
 //
 // reference: PyTorchCPURenderer.render_image / _render_ray_chunk (src/benchmark/
 // pytorch_renderers.py:127-170), NeRFModel.forward (src/models/nerf.py:92-131),
 // execute_volume_rendering (pytorch_renderers.py:105-125).
 #include <cstdlib>
+#include <utility>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,7 +51,8 @@ using namespace ptx;
 
 constexpr int kThreads = 512;
 constexpr int kTileM = 128;
-constexpr int kWStages = 5;
+constexpr int kWStages = 4;
+static_assert(kStagesPerTile % kWStages == 0, "ring slots and barrier parities are compile-time per tile");
 constexpr int kMaxRaysPerTile = 8;      // S_pad >= 16
 
 // shared memory map (bytes from a 1024-aligned base)
@@ -67,11 +73,11 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kWStages, B_PEFULL = B_WEMPTY + kWStages, B_PEEMPTY = B_PEFULL + 2,
-       B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 4, B_FINFULL = B_AREADY + 4, B_FINEMPTY = B_FINFULL + 2,
+       B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 2, B_FINFULL = B_AREADY + 4, B_FINEMPTY = B_FINFULL + 2,
        B_COUNT = B_FINEMPTY + 2 };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 
-__constant__ ChunkTable kChunks = make_chunk_table();
+constexpr ChunkTable kChunks = make_chunk_table();
 
 enum { SRC_RAYS = 1, SRC_POSE = 2 };
 
@@ -92,9 +98,9 @@ struct Args {
 };
 constexpr int kTraceTiles = 6;
 // trace layout: [tile][layer 0..8][slot 0..7] clock64 stamps
-//   0 MMA: first chunk of the layer issued   1 MMA: quarter 0 committed   2 MMA: last quarter committed
-//   3 EPI(warp 4): quarter 0 acc_full seen   4 EPI: quarter 0 a_ready arrive   5 EPI: last quarter done
-//   6 MMA: stalled cycles waiting for a_ready in this layer   7 MMA: stalled cycles waiting for w_full
+//   0 MMA: first chunk of the layer issued   1 MMA: half 0 committed   2 MMA: last half committed
+//   3 EPI(warp 4): half 0 acc_full seen   4 EPI: half 0 a_ready arrive   5 EPI: layer done
+//   6 EPI: last half acc_full seen
 #define TC_TRACE(tile, layer, slot) do { if (a.trace && blockIdx.x == 0 && (tile) < kTraceTiles) a.trace[((tile) * 9 + (layer)) * 8 + (slot)] = clock64(); } while (0)
 
 constexpr long long kTimeoutCycles = 4000000000LL;
@@ -340,16 +346,14 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue of one N=64 accumulator quarter for one warp (32 rows x 32 columns): tcgen05.ld,
-// + bias, ReLU, bf16, and tcgen05.st of the 16 packed columns back over the first half of the
-// columns this warp has just read (the next layer's A operand, K-major in TMEM).
+// epilogue of one N=128 accumulator half for one warp (32 rows x 64 columns): tcgen05.ld,
+// + bias, ReLU, bf16, and tcgen05.st of the 32 packed columns back over the first half of the
+// columns this warp has just read = one K-block of the next layer's A operand (K-major in TMEM).
 // kSigma (layer 7 only) also accumulates the density-head dot product from the fp32 values.
 template <bool kSigma>
-__device__ __forceinline__ void epilogue_quarter(uint32_t t_cols, uint32_t bias_addr, uint32_t wsig_addr, float &sig)
+__device__ __forceinline__ void bias_relu_pack(const uint32_t (&x)[32], uint32_t *pk, uint32_t bias_addr,
+                                               uint32_t wsig_addr, float &sig)
 {
-    uint32_t x[32], pk[16];
-    tmem_ld32(t_cols, x);
-    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float4 b = ld_shared_f4(bias_addr + 16 * i);
@@ -365,17 +369,24 @@ __device__ __forceinline__ void epilogue_quarter(uint32_t t_cols, uint32_t bias_
             sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
         }
     }
-    tmem_st16(t_cols, pk);
+}
+template <bool kSigma>
+__device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t wsig_addr, float &sig)
+{
+    uint32_t xa[32], xb[32], pk[32];
+    tmem_ld32(t_cols, xa);
+    tmem_ld32(t_cols + 32, xb);
+    tmem_ld_wait();
+    bias_relu_pack<kSigma>(xa, pk, bias_addr, wsig_addr, sig);
+    bias_relu_pack<kSigma>(xb, pk + 16, bias_addr + 128, wsig_addr + 128, sig);
+    tmem_st32(t_cols, pk);
     tmem_st_wait();
 }
 
-// colour layer 0, one quarter (32 of this warp's columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
-__device__ __forceinline__ void epilogue_color_quarter(uint32_t t_cols, uint32_t rayb_addr, uint32_t wc1_addr,
-                                                       float &r0, float &r1, float &r2)
+// colour layer 0 (N = 128; this warp: 64 columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
+__device__ __forceinline__ void color_dot(const uint32_t (&x)[32], uint32_t rayb_addr, uint32_t wc1_addr,
+                                          float &r0, float &r1, float &r2)
 {
-    uint32_t x[32];
-    tmem_ld32(t_cols, x);
-    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float4 b = ld_shared_f4(rayb_addr + 16 * i);
@@ -391,6 +402,74 @@ __device__ __forceinline__ void epilogue_color_quarter(uint32_t t_cols, uint32_t
         r1 = fmaf(x0, w1.x, r1); r1 = fmaf(x1, w1.y, r1); r1 = fmaf(x2, w1.z, r1); r1 = fmaf(x3, w1.w, r1);
         r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
     }
+}
+__device__ __forceinline__ void epilogue_color(uint32_t t_cols, uint32_t rayb_addr, uint32_t wc1_addr,
+                                               float &r0, float &r1, float &r2)
+{
+    uint32_t xa[32], xb[32];
+    tmem_ld32(t_cols, xa);
+    tmem_ld32(t_cols + 32, xb);
+    tmem_ld_wait();
+    r0 = r1 = r2 = 0.f;
+    color_dot(xa, rayb_addr, wc1_addr, r0, r1, r2);
+    color_dot(xb, rayb_addr + 128, wc1_addr + 128, r0, r1, r2);
+}
+
+// ------------------------------------------------------------------------------------------
+// MMA issue: one tile's schedule as straight-line code.  Everything that depends on the chunk index
+// is a compile-time constant; the per-tile variables live in IssueCtx.
+struct IssueCtx {
+    uint32_t bars;          // shared address of barrier 0
+    uint32_t region[2];     // TMEM base of the accumulator region of even / odd layers of this tile
+    uint64_t wdesc;         // smem descriptor of weight ring slot 0, chunk 0
+    uint64_t pedesc;        // smem descriptor of this tile's encoded-position operand
+    uint32_t pe_empty_bar;  // barrier released when layer 4 has consumed the encoded position
+    unsigned int *dbg;
+    long long *trace;       // this tile's trace rows or nullptr
+};
+
+template <int CI>
+__device__ __forceinline__ void issue_chunk(const IssueCtx &x)
+{
+    constexpr ChunkInfo c = kChunks.c[CI];
+    constexpr int stage = CI / kStageChunks, slot = stage % kWStages;
+    constexpr uint32_t idesc = idesc_bf16(128, 128);
+    constexpr bool last_of_layer = CI + 1 == kChunksPerTile || kChunks.c[CI + 1 < kChunksPerTile ? CI + 1 : CI].layer != c.layer;
+    constexpr bool first_of_layer = CI == 0 || kChunks.c[CI > 0 ? CI - 1 : 0].layer != c.layer;
+    if constexpr (CI % kStageChunks == 0)
+        wait_bar(x.bars + 8u * (B_WFULL + slot), (stage / kWStages) & 1, x.dbg, 4);
+    if constexpr ((c.flags & 4) != 0)      // a_ready[kb]: one phase per producing layer 0..7 (8 per tile: parity restarts)
+        wait_bar(x.bars + 8u * (B_AREADY + c.asrc), (c.layer - 1) & 1, x.dbg, 3);
+    tc_fence_after_sync();
+    if (elect_one()) {
+        const uint32_t d_tmem = x.region[c.layer & 1] + c.half * 128;
+        const uint64_t bdesc = x.wdesc + (uint64_t)((slot * kStageBytes + (CI % kStageChunks) * kChunkBytes) >> 4);
+        if constexpr (c.asrc == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)          // 4 x (K = 16): +32 B inside the 128 B swizzle span
+                mma_bf16_ss(d_tmem, x.pedesc + 2 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
+        } else {
+            // A = K-block `asrc` of the previous layer: bf16 pairs written in place over the other
+            // region's accumulator columns [64 asrc, 64 asrc + 32)
+            const uint32_t a_tmem = x.region[(c.layer & 1) ^ 1] + c.asrc * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_bf16_ts(d_tmem, a_tmem + 8 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
+        }
+        if constexpr (first_of_layer) { if (x.trace) x.trace[c.layer * 8 + 0] = clock64(); }
+        if constexpr ((c.flags & 2) != 0) {
+            mma_commit(x.bars + 8u * (B_ACCFULL + c.half));
+            if (x.trace) x.trace[c.layer * 8 + (last_of_layer ? 2 : 1)] = clock64();
+        }
+        if constexpr (CI % kStageChunks == kStageChunks - 1) mma_commit(x.bars + 8u * (B_WEMPTY + slot));
+        if constexpr (c.layer == 4 && last_of_layer) mma_commit(x.pe_empty_bar);
+    }
+    __syncwarp();
+}
+template <int... CI>
+__device__ __forceinline__ void issue_tile(const IssueCtx &x, std::integer_sequence<int, CI...>)
+{
+    (issue_chunk<CI>(x), ...);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -419,7 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
             mbar_init(bar(B_FINFULL + i), 8); mbar_init(bar(B_FINEMPTY + i), 4);
         }
-        for (int i = 0; i < 4; ++i) { mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_AREADY + i), 8); }
+        for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACCFULL + i), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), 4);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(sm_base + SM_TMEM);
@@ -453,122 +533,72 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         }
     } else if (warp == 1) {
         // ================================ MMA issuer =========================================
-        if (lane == 0) {
-            uint32_t sg = 0, g = 0;
-            const uint32_t idesc = idesc_bf16(128, 64);
-            for (int t = 0; t < my_tiles; ++t) {
-                const int pb = t & 1;
-                wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 2);
-                uint32_t kb_seen = 0;               // a_ready[kb] already waited for in this layer
-                int cur_layer = 0;
-                long long stall_a = 0, stall_w = 0;
-                for (int ci = 0; ci < kChunksPerTile; ++ci) {
-                    const ChunkInfo c = kChunks.c[ci];
-                    if (c.layer != cur_layer) {
-                        cur_layer = c.layer; kb_seen = 0; ++g;
-                        stall_a = stall_w = 0;
-                    }
-                    const uint32_t slot = sg % kWStages;
-                    if ((ci & 3) == 0) {
-                        const long long t0 = a.trace ? clock64() : 0;
-                        wait_bar(bar(B_WFULL + slot), (sg / kWStages) & 1, a.dbg, 4);
-                        if (a.trace) stall_w += clock64() - t0;
-                    }
-                    if (c.asrc < 4 && !(kb_seen & (1u << c.asrc))) {
-                        const long long t0 = a.trace ? clock64() : 0;
-                        // a_ready[kb] completes once per producing layer (0..7: 8 phases per tile, so the parity
-                        // restarts every tile); layer l consumes the phase produced by layer l-1
-                        wait_bar(bar(B_AREADY + c.asrc), (c.layer - 1) & 1, a.dbg, 3);
-                        if (a.trace) stall_a += clock64() - t0;
-                        kb_seen |= 1u << c.asrc;
-                    }
-                    tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + (g & 1) * 256 + c.nq * 64;
-                    const uint64_t bdesc = smem_desc_sw128(sm_base + SM_W + slot * kStageBytes + (ci & 3) * kChunkBytes);
-                    if (c.asrc == 4) {
-                        const uint64_t adesc = smem_desc_sw128(sm_base + SM_PE + pb * 16384);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)      // 4 x (K = 16): +32 B inside the 128 B swizzle span
-                            mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
-                    } else {
-                        // A = previous layer's quarter `asrc`, bf16 in place in the other TMEM region:
-                        // K 0..31 in columns +0..15 (written by the half-0 warps), K 32..63 in columns +32..47
-                        const uint32_t a_tmem = tmem_base + ((g & 1) ^ 1) * 256 + c.asrc * 64;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_bf16_ts(d_tmem, a_tmem + (k >> 1) * 32 + (k & 1) * 8, bdesc + 2 * k, idesc,
-                                        !((c.flags & 1) && k == 0));
-                    }
-                    if (c.flags & 1) { if (c.nq == 0) TC_TRACE(t, c.layer, 0); }
-                    if (c.flags & 2) {
-                        mma_commit(bar(B_ACCFULL + c.nq));
-                        if (c.nq == 0) TC_TRACE(t, c.layer, 1);
-                        if (c.nq == (c.layer == 8 ? 1 : 3)) {
-                            TC_TRACE(t, c.layer, 2);
-                            if (a.trace && blockIdx.x == 0 && t < kTraceTiles) {
-                                a.trace[(t * 9 + c.layer) * 8 + 6] = stall_a;
-                                a.trace[(t * 9 + c.layer) * 8 + 7] = stall_w;
-                            }
-                        }
-                    }
-                    if ((ci & 3) == 3) { mma_commit(bar(B_WEMPTY + slot)); ++sg; }
-                    if (c.layer == 4 && (c.flags & 2) && c.nq == 3) mma_commit(bar(B_PEEMPTY + pb));
-                }
-                ++g;                                // next tile's layer 0
-            }
+        // warp-uniform control flow; one elected lane issues the tcgen05 instructions
+        IssueCtx x;
+        x.bars = bars;
+        x.wdesc = smem_desc_sw128(sm_base + SM_W);
+        x.dbg = a.dbg;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int pb = t & 1;
+            wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 2);
+            // nine layers per tile: the region parity of layer l of tile t is (t + l) & 1
+            x.region[0] = tmem_base + (uint32_t)(t & 1) * 256;
+            x.region[1] = tmem_base + (uint32_t)((t & 1) ^ 1) * 256;
+            x.pedesc = smem_desc_sw128(sm_base + SM_PE + pb * 16384);
+            x.pe_empty_bar = bar(B_PEEMPTY + pb);
+            x.trace = (a.trace && blockIdx.x == 0 && t < kTraceTiles) ? a.trace + t * 72 : nullptr;
+            issue_tile(x, std::make_integer_sequence<int, kChunksPerTile>{});
         }
     } else if (warp >= 4 && warp < 12) {
         // ================================ epilogue ===========================================
-        const int ew = warp - 4, q = ew & 3, h = ew >> 2;
+        const int ew = warp - 4, q = ew & 3, w2 = ew >> 2;
         const int row = q * 32 + lane;
-        uint32_t g = 0, acc_uses[4] = {0, 0, 0, 0};
+        uint32_t g = 0, acc_uses[2] = {0, 0};
         for (int t = 0; t < my_tiles; ++t) {
             const int pb = t & 1, fb = t & 1;
             float *fin = reinterpret_cast<float *>(sm + SM_FIN + fb * 4096 + row * 32);
+            long long *tr = (a.trace && blockIdx.x == 0 && t < kTraceTiles && ew == 0 && lane == 0) ? a.trace + t * 72 : nullptr;
             for (int layer = 0; layer < 9; ++layer, ++g) {
-                const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 32 * h;
+                const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
                 if (layer < 8) {
                     float sig = 0.f;
 #pragma unroll
-                    for (int nq = 0; nq < 4; ++nq) {
-                        wait_bar(bar(B_ACCFULL + nq), acc_uses[nq] & 1, a.dbg, 5);
-                        ++acc_uses[nq];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        wait_bar(bar(B_ACCFULL + hh), acc_uses[hh] & 1, a.dbg, 5);
+                        ++acc_uses[hh];
                         tc_fence_after_sync();
-                        if (nq == 0 && ew == 0 && lane == 0) TC_TRACE(t, layer, 3);
-                        const uint32_t col = layer * 256 + nq * 64 + 32 * h;
+                        if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
+                        const uint32_t n0 = hh * 128 + 64 * w2;
                         if (layer == 7)
-                            epilogue_quarter<true>(t_lane + nq * 64, sm_base + SM_BIAS + col * 4,
-                                                   sm_base + SM_WSIG + (nq * 64 + 32 * h) * 4, sig);
+                            epilogue_half<true>(t_lane + hh * 128, sm_base + SM_BIAS + (7 * 256 + n0) * 4,
+                                                sm_base + SM_WSIG + n0 * 4, sig);
                         else
-                            epilogue_quarter<false>(t_lane + nq * 64, sm_base + SM_BIAS + col * 4, 0, sig);
+                            epilogue_half<false>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + n0) * 4, 0, sig);
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(B_AREADY + nq));
-                        if (nq == 0 && ew == 0 && lane == 0) TC_TRACE(t, layer, 4);
+                        if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
+                        if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                     }
                     if (layer == 7) {
                         if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
-                        fin[h] = sig;
+                        fin[w2] = sig;
                     }
                 } else {
                     wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
+                    wait_bar(bar(B_ACCFULL + 0), acc_uses[0] & 1, a.dbg, 5);
+                    ++acc_uses[0];
+                    tc_fence_after_sync();
+                    if (tr) tr[layer * 8 + 3] = clock64();
                     const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
-                    const uint32_t rayb = sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512;
-                    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-                    for (int nq = 0; nq < 2; ++nq) {
-                        wait_bar(bar(B_ACCFULL + nq), acc_uses[nq] & 1, a.dbg, 5);
-                        ++acc_uses[nq];
-                        tc_fence_after_sync();
-                        const uint32_t n0 = nq * 64 + 32 * h;
-                        epilogue_color_quarter(t_lane + nq * 64, rayb + n0 * 4, sm_base + SM_WC1 + n0 * 4, r0, r1, r2);
-                    }
-                    fin[2 + 3 * h + 0] = r0; fin[2 + 3 * h + 1] = r1; fin[2 + 3 * h + 2] = r2;
+                    const uint32_t rayb = sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512 + w2 * 256;
+                    float r0, r1, r2;
+                    epilogue_color(t_lane, rayb, sm_base + SM_WC1 + w2 * 256, r0, r1, r2);
+                    fin[2 + 3 * w2 + 0] = r0; fin[2 + 3 * w2 + 1] = r1; fin[2 + 3 * w2 + 2] = r2;
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(B_FINFULL + fb));
                 }
-                if (ew == 0 && lane == 0) TC_TRACE(t, layer, 5);
+                if (tr) tr[layer * 8 + 5] = clock64();
             }
         }
     } else if (warp >= 12) {

@@ -12,7 +12,7 @@ __constant__ ChunkTable kPackTable = make_chunk_table();
 __device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int ci)
 {
     const ChunkInfo c = kPackTable.c[ci];
-    const int n0 = 64 * c.nq;
+    const int n0 = 128 * c.half;
     if (c.layer == 0) return {p.layer_w[0], 63, n0, 0, 63};
     if (c.layer == 8) return {p.color0_w, 283, n0, 64 * c.asrc, 64};
     if (c.layer == 4) return c.asrc == 4 ? ChunkSrc{p.layer_w[4], 319, n0, 256, 63}
@@ -48,9 +48,9 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
     }
 
     // ---- bf16 region: one 16-byte unit (8 consecutive k of one row) per thread-iteration ----
-    const size_t units = (size_t)kChunksPerTile * 64 * 8;
+    const size_t units = (size_t)kChunksPerTile * 128 * 8;
     for (size_t uidx = tid; uidx < units; uidx += nth) {
-        const int ci = (int)(uidx / 512), n = (int)((uidx % 512) / 8), unit = (int)(uidx % 8);
+        const int ci = (int)(uidx / 1024), n = (int)((uidx % 1024) / 8), unit = (int)(uidx % 8);
         const ChunkSrc src = chunk_source(p, ci);
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll

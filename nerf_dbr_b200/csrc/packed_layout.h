@@ -37,27 +37,32 @@ constexpr size_t F_END = F_WC0D + 32 * 128;
 __host__ __device__ constexpr size_t f_wt(int layer) { return F_WT + (size_t)(layer - 1) * 256 * 256; }
 
 // ---- bf16 region --------------------------------------------------------------------------
-// The tcgen05 kernel computes every layer as N = 64 output-column quarters (4 per 256-wide layer,
-// 2 for colour layer 0) and streams the weights as [64 n x 64 k] bf16 chunks (8 KB, 128B-swizzled
-// K-major) in EXACTLY the order its MMA issuer consumes them, so the producer warp just copies
-// consecutive 32 KB stages (4 chunks).  Per 128-sample tile: 128 chunks = 32 stages = 1 MiB.
+// The tcgen05 kernel computes every 256-wide layer as two N = 128 output-column halves (one MMA
+// instruction = M128 x N128 x K16 = 64 tensor-pipe cycles; narrower instructions fall below the
+// pipe's ~46-cycle issue floor, tools/probe/mma_probe.cu) and streams the weights as
+// [128 n x 64 k] bf16 chunks (16 KB, 128B-swizzled K-major) in EXACTLY the order its MMA issuer
+// consumes them, so the producer warp just copies consecutive 32 KB stages (2 chunks).
+// Per 128-sample tile: 64 chunks = 32 stages = 1 MiB.
 //
-// Order inside a layer ("N-outer, last K-block late"): quarters 0 and 1 first take K-blocks
-// 0,1,2 (and the encoded-position chunk, layer 4), then K-block 3 of both, then quarters 2 and 3
-// in plain order.  Quarter accumulators therefore complete one after another (their epilogues
-// overlap the layer's remaining MMAs) and the previous layer's LAST quarter -- whose epilogue
-// finishes last -- is not needed before the 7th chunk.
-constexpr int kChunkBytes = 64 * 128;                         // [64 x 64] bf16
-constexpr int kChunksPerTile = 128;
-constexpr int kStageChunks = 4;
+// Order inside a layer:  h0k0 h0k1 h1k0 h0k2 h0k3 h1k1 h1k2 h1k3   (h = output half, k = K-block)
+//   * K-blocks 0,1 of the input are the previous layer's half 0, K-blocks 2,3 its half 1 (whose
+//     epilogue finishes last): nothing before the 4th chunk needs them -> ~770 cycles of slack.
+//   * half 0 completes after the 5th chunk, so its epilogue (bias, ReLU, bf16, write-back) is done
+//     before the layer ends; half 1's epilogue overlaps the next layer's first three chunks.
+//   layer 4 adds an encoded-position chunk per half (no dependency); layer 0 is those alone;
+//   colour layer 0 has one half.
+constexpr int kChunkBytes = 128 * 128;                        // [128 x 64] bf16
+constexpr int kChunksPerTile = 64;
+constexpr int kStageChunks = 2;
 constexpr int kStageBytes = kStageChunks * kChunkBytes;       // 32 KB
 constexpr int kStagesPerTile = kChunksPerTile / kStageChunks; // 32
 
 struct ChunkInfo {
     uint8_t layer;   // 0..7 trunk, 8 = colour layer 0
-    uint8_t nq;      // output quarter: columns [64 nq, 64 nq + 64)
-    uint8_t asrc;    // A operand: 0..3 = hidden K-block (previous layer's quarter), 4 = encoded position
-    uint8_t flags;   // 1 = first chunk of this quarter (overwrite), 2 = last chunk of this quarter
+    uint8_t half;    // output half: columns [128 half, 128 half + 128)
+    uint8_t asrc;    // A operand: 0..3 = hidden K-block of the previous layer, 4 = encoded position
+    uint8_t flags;   // 1 = first chunk of this half (overwrite), 2 = last chunk of this half,
+                     // 4 = first use of this A K-block in the layer (wait for its epilogue)
 };
 struct ChunkTable { ChunkInfo c[kChunksPerTile]; };
 
@@ -66,35 +71,40 @@ constexpr ChunkTable make_chunk_table()
     ChunkTable t{};
     int n = 0;
     for (int layer = 0; layer < 9; ++layer) {
-        const int quarters = layer == 8 ? 2 : 4;
-        const bool pe = layer == 4;
         const int begin = n;
+        const int halves = layer == 8 ? 1 : 2;
         if (layer == 0) {
-            for (int q = 0; q < 4; ++q) t.c[n++] = ChunkInfo{0, (uint8_t)q, 4, 3};
-            continue;
+            t.c[n++] = ChunkInfo{0, 0, 4, 0};
+            t.c[n++] = ChunkInfo{0, 1, 4, 0};
+        } else if (layer == 8) {
+            for (int kb = 0; kb < 4; ++kb) t.c[n++] = ChunkInfo{8, 0, (uint8_t)kb, 0};
+        } else {
+            const uint8_t L = (uint8_t)layer;
+            if (layer == 4) t.c[n++] = ChunkInfo{L, 0, 4, 0};
+            t.c[n++] = ChunkInfo{L, 0, 0, 0};
+            t.c[n++] = ChunkInfo{L, 0, 1, 0};
+            if (layer == 4) t.c[n++] = ChunkInfo{L, 1, 4, 0};
+            t.c[n++] = ChunkInfo{L, 1, 0, 0};
+            t.c[n++] = ChunkInfo{L, 0, 2, 0};
+            t.c[n++] = ChunkInfo{L, 0, 3, 0};
+            t.c[n++] = ChunkInfo{L, 1, 1, 0};
+            t.c[n++] = ChunkInfo{L, 1, 2, 0};
+            t.c[n++] = ChunkInfo{L, 1, 3, 0};
         }
-        for (int q = 0; q < 2; ++q) {
-            if (pe) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, 4, 0};
-            for (int kb = 0; kb < 3; ++kb) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, (uint8_t)kb, 0};
-        }
-        t.c[n++] = ChunkInfo{(uint8_t)layer, 0, 3, 0};
-        t.c[n++] = ChunkInfo{(uint8_t)layer, 1, 3, 0};
-        for (int q = 2; q < quarters; ++q) {
-            if (pe) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, 4, 0};
-            for (int kb = 0; kb < 4; ++kb) t.c[n++] = ChunkInfo{(uint8_t)layer, (uint8_t)q, (uint8_t)kb, 0};
-        }
-        // first / last chunk of every quarter of this layer
-        for (int q = 0; q < quarters; ++q) {
+        for (int h = 0; h < halves; ++h) {
             int first = -1, last = -1;
             for (int i = begin; i < n; ++i)
-                if (t.c[i].nq == q) { if (first < 0) first = i; last = i; }
+                if (t.c[i].half == h) { if (first < 0) first = i; last = i; }
             t.c[first].flags |= 1;
             t.c[last].flags |= 2;
         }
+        for (int kb = 0; kb < 4; ++kb)
+            for (int i = begin; i < n; ++i)
+                if (t.c[i].asrc == kb) { t.c[i].flags |= 4; break; }
     }
     return t;
 }
-static_assert(make_chunk_table().c[kChunksPerTile - 1].layer == 8, "chunk table must fill exactly 128 entries");
+static_assert(make_chunk_table().c[kChunksPerTile - 1].layer == 8, "chunk table must fill exactly 64 entries");
 
 constexpr size_t B_OFFSET = ((F_END * 4 + 1023) / 1024) * 1024;   // byte offset of the bf16 region
 constexpr size_t B_BYTES = (size_t)kChunksPerTile * kChunkBytes;  // 1 MiB

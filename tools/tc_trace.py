@@ -17,14 +17,14 @@ L.load_library().nerf_b200_set_trace_buffer(ctypes.c_void_p(buf.data_ptr()))
 ops.render_image(net, pose, 800, 600, 128, mode=1)
 torch.cuda.synchronize()
 L.load_library().nerf_b200_set_trace_buffer(None)
-t = buf.cpu().numpy().reshape(6, 9, 8)
-t0 = t[:, :, :6][t[:, :, :6] > 0].min()
-print("tile layer  mma_first  q0_commit last_commit  epi_q0_acc epi_q0_arr  epi_done | stall_a stall_w | layer_period q0commit->acc acc->arrive")
+t = buf.cpu().numpy().reshape(6, 9, 8).astype(np.int64)
+t0 = t[t > 0].min()
+print("slots: mma_first h0_commit last_commit | epi_h0_acc epi_h0_arrive epi_done epi_h1_acc || layer_period  E_h0(acc->arrive)  E_h1(acc->done)")
 for ti in range(2, 6):
     for l in range(9):
-        r = t[ti, l].astype(np.int64)
-        rel = r[:6] - t0
+        r = t[ti, l]
+        rel = np.where(r > 0, r - t0, -1)
         nxt = t[ti, l + 1, 0] if l < 8 else (t[ti + 1, 0, 0] if ti + 1 < 6 else 0)
-        print(f"{ti:4d} {l:5d} " + " ".join(f"{int(v):10d}" for v in rel) + f" | {int(r[6]):7d} {int(r[7]):7d} | "
-              f"{int(nxt - r[0]) if nxt else -1:8d} {int(r[3]-r[1]):10d} {int(r[4]-r[3]):10d}")
+        print(f"{ti:2d} {l:2d} " + " ".join(f"{int(v):9d}" for v in rel[:7]) + f" || {int(nxt - r[0]) if nxt else -1:8d} "
+              f"{int(r[4]-r[3]) if r[4] > 0 else -1:8d} {int(r[5]-r[6]) if r[6] > 0 else -1:8d}")
 print("tile period (cycles):", (t[5, 0, 0] - t[2, 0, 0]) / 3)
