@@ -74,7 +74,11 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kWStages, B_PEFULL = B_WEMPTY + kWStages, B_PEEMPTY = B_PEFULL + 2,
        B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 2, B_FINFULL = B_AREADY + 4, B_FINEMPTY = B_FINFULL + 2,
-       B_COUNT = B_FINEMPTY + 2 };
+       B_ACCC0 = B_FINEMPTY + 2, B_COUNT = B_ACCC0 + 1 };
+// Phase discipline (mbarrier parity waits are only sound while the producer is at most ONE phase ahead of
+// every waiter): acc_full[h] completes once per trunk layer 0..7 and each completion needs the previous
+// layer's epilogue; colour layer 0 has its own barrier because the NEXT tile's layer 0 follows it with no
+// epilogue in between -- sharing acc_full[0] let the barrier run two phases ahead of a slow epilogue warp.
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 
 constexpr ChunkTable kChunks = make_chunk_table();
@@ -458,7 +462,7 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
         }
         if constexpr (first_of_layer) { if (x.trace) x.trace[c.layer * 8 + 0] = clock64(); }
         if constexpr ((c.flags & 2) != 0) {
-            mma_commit(x.bars + 8u * (B_ACCFULL + c.half));
+            mma_commit(x.bars + 8u * (c.layer == 8 ? B_ACCC0 : B_ACCFULL + c.half));
             if (x.trace) x.trace[c.layer * 8 + (last_of_layer ? 2 : 1)] = clock64();
         }
         if constexpr (CI % kStageChunks == kStageChunks - 1) mma_commit(x.bars + 8u * (B_WEMPTY + slot));
@@ -499,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             mbar_init(bar(B_FINFULL + i), 8); mbar_init(bar(B_FINEMPTY + i), 4);
         }
         for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACCFULL + i), 1);
+        mbar_init(bar(B_ACCC0), 1);
         for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), 4);
         fence_mbar_init();
     }
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         // ================================ epilogue ===========================================
         const int ew = warp - 4, q = ew & 3, w2 = ew >> 2;
         const int row = q * 32 + lane;
-        uint32_t g = 0, acc_uses[2] = {0, 0};
+        uint32_t g = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int pb = t & 1, fb = t & 1;
             float *fin = reinterpret_cast<float *>(sm + SM_FIN + fb * 4096 + row * 32);
@@ -564,8 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     float sig = 0.f;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        wait_bar(bar(B_ACCFULL + hh), acc_uses[hh] & 1, a.dbg, 5);
-                        ++acc_uses[hh];
+                        wait_bar(bar(B_ACCFULL + hh), layer & 1, a.dbg, 5);      // 8 phases per tile: parity = layer
                         tc_fence_after_sync();
                         if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
                         const uint32_t n0 = hh * 128 + 64 * w2;
@@ -585,8 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     }
                 } else {
                     wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
-                    wait_bar(bar(B_ACCFULL + 0), acc_uses[0] & 1, a.dbg, 5);
-                    ++acc_uses[0];
+                    wait_bar(bar(B_ACCC0), t & 1, a.dbg, 5);
                     tc_fence_after_sync();
                     if (tr) tr[layer * 8 + 3] = clock64();
                     const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
