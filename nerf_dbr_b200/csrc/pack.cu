@@ -43,7 +43,13 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
         }
         else if (i < F_WC0H) { size_t j = i - F_W4P; int k = (int)(j / 256), n = (int)(j % 256); v = k < 63 ? p.layer_w[4][n * 319 + 256 + k] : 0.f; }
         else if (i < F_WC0D) { size_t j = i - F_WC0H; int k = (int)(j / 128), n = (int)(j % 128); v = p.color0_w[n * 283 + k]; }
-        else { size_t j = i - F_WC0D; int k = (int)(j / 128), n = (int)(j % 128); v = k < 27 ? p.color0_w[n * 283 + 256 + k] : 0.f; }
+        else if (i < F_WO) { size_t j = i - F_WC0D; int k = (int)(j / 128), n = (int)(j % 128); v = k < 27 ? p.color0_w[n * 283 + 256 + k] : 0.f; }
+        else if (i < F_WC0O) {
+            size_t j = i - F_WO; int l = 1 + (int)(j / 65536); j %= 65536;
+            int n = (int)(j / 256), k = (int)(j % 256);
+            v = p.layer_w[l][(size_t)n * (l == 4 ? 319 : 256) + k];
+        }
+        else { size_t j = i - F_WC0O; int n = (int)(j / 256), k = (int)(j % 256); v = p.color0_w[n * 283 + k]; }
         f[i] = v;
     }
 

@@ -33,7 +33,11 @@ constexpr size_t F_WT = F_W0T + 64 * 256;                     // 7 x [256][256]:
 constexpr size_t F_W4P = F_WT + 7 * 256 * 256;                // [64][256]  layer 4, encoded-position part
 constexpr size_t F_WC0H = F_W4P + 64 * 256;                   // [256][128] colour-0, hidden part
 constexpr size_t F_WC0D = F_WC0H + 256 * 128;                 // [32][128]  colour-0, encoded-direction part (rows 27..31 = 0)
-constexpr size_t F_END = F_WC0D + 32 * 128;
+constexpr size_t F_WO = F_WC0D + 32 * 128;                    // 7 x [256 out][256 in]: layers 1..7 in nn.Linear order (layer 4:
+                                                              // hidden columns only) -- the dgrad operand of the training step
+constexpr size_t F_WC0O = F_WO + 7 * 256 * 256;               // [128 out][256 in] colour-0, hidden columns
+constexpr size_t F_END = F_WC0O + 128 * 256;
+__host__ __device__ constexpr size_t f_wo(int layer) { return F_WO + (size_t)(layer - 1) * 256 * 256; }
 __host__ __device__ constexpr size_t f_wt(int layer) { return F_WT + (size_t)(layer - 1) * 256 * 256; }
 
 // ---- bf16 region --------------------------------------------------------------------------

@@ -182,5 +182,46 @@ def render_rays(packed: torch.Tensor, rays_o, rays_d, n_samples: int, mode: int 
     return (rgb, depth, acc) if want_acc else (rgb, depth)
 
 
+_workspaces = {}
+
+
+def train_fwd_bwd(model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_rays_global: Optional[int] = None,
+                  near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True):
+    """Forward + backward of one network's loss term mean((C - target)^2) (reference
+    NeRFTrainer.train_step, trainer.py:117-126).  ``model`` is a CUDA ``NeRFModel`` (or any module with the
+    reference's parameter names); d loss/d params is accumulated into ``p.grad`` (created as zeros when
+    None) -- scaled for ``n_rays_global`` rays so data-parallel ranks can all-reduce-sum.  Returns
+    (loss_term as a 0-dim tensor computed over this call's rays with the global normaliser, rgb [R,3])."""
+    lib = L.load_library()
+    ro, rd, tg = _dev(rays_o, "train_fwd_bwd"), _dev(rays_d, "train_fwd_bwd"), _dev(target, "train_fwd_bwd")
+    n = ro.shape[0]
+    n_global = n if n_rays_global is None else n_rays_global
+    dev = ro.device
+    named = dict(model.named_parameters())
+    params, grads = {}, {}
+    for k in STATE_ORDER:
+        p = named[k]
+        if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+            raise L.NerfB200Error("train_fwd_bwd", -101, f"parameter {k} must be a contiguous fp32 CUDA tensor")
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        params[k], grads[k] = p.detach(), p.grad
+    packed = pack_weights(params, dev)
+    nbytes = lib.nerf_b200_train_workspace_bytes(n, n_samples)
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _workspaces[dev] = ws
+    loss_sum = torch.zeros(1, device=dev)
+    rgb = torch.empty(n, 3, device=dev) if want_rgb else None
+    tr = None if t_rand is None else _dev(t_rand, "train_fwd_bwd")
+    ps, gs = params_struct(params), params_struct(grads)
+    with torch.cuda.device(dev):
+        L.check("nerf_b200_train_fwd_bwd", lib.nerf_b200_train_fwd_bwd(
+            _ptr(packed), ctypes.byref(ps), ctypes.byref(gs), _ptr(ro), _ptr(rd), _ptr(tg), n, n_samples, near, far,
+            _ptr(tr), n_global, mode, _ptr(ws), _ptr(loss_sum), _ptr(rgb), _stream()))
+    return loss_sum[0] / (3.0 * n_global), rgb
+
+
 def launch_count() -> int:
     return int(L.load_library().nerf_b200_launch_count())

@@ -1,0 +1,51 @@
+"""Training step on the B200 kernels with the reference trainer's semantics
+(src/training/trainer.py:83-138, 294-316): coarse network on ``n_coarse`` stratified samples, fine
+network on ``n_fine`` uniform samples, loss = mse(coarse) + mse(fine); the optimizer, gradient clipping
+and LR schedule stay plain PyTorch on the same ``nn.Parameter``s (trainer.py:125-136)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+from . import ops
+from .model import NeRFModel
+
+
+class B200TrainStep:
+    """Replaces NeRFTrainer._render_rays + loss + backward.  Data parallel: every rank passes its
+    shard of the ray batch and the GLOBAL ray count; gradients are all-reduce-summed over NCCL."""
+
+    def __init__(self, coarse: NeRFModel, fine: NeRFModel, n_coarse: int = 64, n_fine: int = 128,
+                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32):
+        self.coarse, self.fine = coarse, fine
+        self.n_coarse, self.n_fine, self.near, self.far, self.mode = n_coarse, n_fine, near, far, mode
+
+    def parameters(self):
+        return list(self.coarse.parameters()) + list(self.fine.parameters())
+
+    def __call__(self, rays_o, rays_d, target, t_rand: Optional[torch.Tensor] = None,
+                 n_rays_global: Optional[int] = None, allreduce: bool = True):
+        """Zeroes the gradients, runs forward+backward of both networks, all-reduces when a process
+        group is initialised, returns (loss, rgb_coarse, rgb_fine)."""
+        for p in self.parameters():
+            if p.grad is not None:
+                p.grad.zero_()
+        if t_rand is None:                       # the reference jitters the coarse samples (rendering.py:46)
+            t_rand = torch.rand(rays_o.shape[0], self.n_coarse, device=rays_o.device)
+        lc, rgb_c = ops.train_fwd_bwd(self.coarse, rays_o, rays_d, target, self.n_coarse, t_rand, n_rays_global,
+                                      self.near, self.far, self.mode)
+        lf, rgb_f = ops.train_fwd_bwd(self.fine, rays_o, rays_d, target, self.n_fine, None, n_rays_global,
+                                      self.near, self.far, self.mode)
+        loss = lc + lf
+        if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in self.parameters()] + [loss.reshape(1)])
+            dist.all_reduce(flat)                # one 4.24 MB sum over NVLink
+            off = 0
+            for p in self.parameters():
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            loss = flat[-1]
+        return loss, rgb_c, rgb_f

@@ -1,0 +1,120 @@
+"""GPU: the training step's forward+backward against the reference's autograd (golden fixture from
+NeRFTrainer.train_step) and against the oracle on small ragged cases."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+REL = 2e-4          # per-tensor relative L2 error of a gradient vs fp32 autograd on the CPU
+
+
+def models_from(ck):
+    import nerf_dbr_b200 as nb
+    c, f = nb.NeRFModel().cuda(), nb.NeRFModel().cuda()
+    c.load_state_dict(ck["coarse_model"])
+    f.load_state_dict(ck["fine_model"])
+    return c, f
+
+
+def test_train_step_matches_reference_golden():
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    g = load_npz("golden_train.npz")
+    ck = O.seeded_checkpoint(int(g["seed"]), float(g["density_gain"]))
+    coarse, fine = models_from(ck)
+    H, W = int(g["H"]), int(g["W"])
+    image = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(0))
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+    ro, rd = O.camera_rays(pose, W, H)
+    sel = torch.from_numpy(g["select"])
+    ro, rd, tgt = ro.reshape(-1, 3)[sel].cuda(), rd.reshape(-1, 3)[sel].cuda(), image.reshape(-1, 3)[sel].cuda()
+    step = B200TrainStep(coarse, fine, 64, 128)
+    loss, rgb_c, rgb_f = step(ro, rd, tgt, t_rand=torch.from_numpy(g["t_rand"]).cuda())
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    worst = 0.0
+    for tag, m in (("coarse", coarse), ("fine", fine)):
+        for name, p in m.named_parameters():
+            ref_norm = float(g[f"{tag}|{name}|norm"])
+            got = p.grad.reshape(-1).cpu()
+            ref = torch.from_numpy(g[f"{tag}|{name}|strided"])
+            err = float((got[::37] - ref).double().norm()) / max(float(ref.double().norm()), 1e-30)
+            nerr = abs(float(got.double().norm()) - ref_norm) / max(ref_norm, 1e-30)
+            worst = max(worst, err, nerr)
+            assert err <= REL and nerr <= REL, (tag, name, err, nerr)
+    print("worst relative gradient error vs reference autograd:", worst)
+
+
+@pytest.mark.parametrize("n_rays,S,jitter", [(37, 16, True), (130, 64, False), (65, 100, True), (9, 200, False)])
+def test_train_fwd_bwd_vs_oracle_autograd(n_rays, S, jitter, checkpoints, poses):
+    """Ragged ray counts and sample counts, trained-magnitude weights (saturated alphas), accumulation
+    into existing grads, global-count scaling (the data-parallel contract)."""
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import ops
+    w = checkpoints["semi30"]["fine_model"]
+    ro, rd = O.camera_rays(poses["generic"], 23, 11)
+    gen = torch.Generator().manual_seed(n_rays)
+    idx = torch.randperm(ro.reshape(-1, 3).shape[0], generator=gen)[:n_rays]
+    ro, rd = ro.reshape(-1, 3)[idx].contiguous(), rd.reshape(-1, 3)[idx].contiguous()
+    tgt = torch.rand(n_rays, 3, generator=gen)
+    tr = torch.rand(n_rays, S, generator=gen) if jitter else None
+    # oracle: one network's term, autograd
+    wt = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    pts, z = O.sample_along_rays(ro, rd, S, t_rand=tr)
+    sg, col = O.mlp(wt, pts.reshape(-1, 3), rd[:, None, :].expand_as(pts).reshape(-1, 3))
+    rgb_ref = O.composite(sg.reshape(n_rays, S, 1), col.reshape(n_rays, S, 3), z, rd)[0]
+    n_global = 3 * n_rays
+    loss_ref = ((rgb_ref - tgt) ** 2).sum() / (3 * n_global)
+    loss_ref.backward()
+    m = nb.NeRFModel().cuda()
+    m.load_state_dict(w)
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)                                   # accumulation contract: += into grads
+    loss, rgb = ops.train_fwd_bwd(m, ro.cuda(), rd.cuda(), tgt.cuda(), S, None if tr is None else tr.cuda(),
+                                  n_rays_global=n_global)
+    assert (rgb.cpu() - rgb_ref.detach()).abs().max() <= 1e-4
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(float(loss_ref), 1e-12)
+    for name, p in m.named_parameters():
+        got = (p.grad - 1.0).cpu().double()
+        ref = wt[name].grad.double()
+        scale = max(float(ref.norm()), 1e-12)
+        assert float((got - ref).norm()) / scale <= 2e-3 or float((got - ref).abs().max()) <= 1e-9, name
+
+
+def test_adam_step_follows_reference_trainer(checkpoints):
+    """Three optimizer steps with the unchanged torch Adam on top of the CUDA gradients track the
+    oracle's CPU training loop (same jitter, same batches)."""
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    ck = O.seeded_checkpoint(5, 30.0)
+    coarse, fine = models_from(ck)
+    step = B200TrainStep(coarse, fine, 32, 64)
+    opt = torch.optim.Adam(step.parameters(), lr=5e-4)
+    cw = {k: v.clone() for k, v in ck["coarse_model"].items()}
+    fw = {k: v.clone() for k, v in ck["fine_model"].items()}
+    cpu_params = [torch.nn.Parameter(v) for v in list(cw.values()) + list(fw.values())]
+    cpu_opt = torch.optim.Adam(cpu_params, lr=5e-4)
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+    ro_all, rd_all = O.camera_rays(pose, 40, 30)
+    gen = torch.Generator().manual_seed(1)
+    for it in range(3):
+        sel = torch.randperm(1200, generator=gen)[:96]
+        ro, rd = ro_all.reshape(-1, 3)[sel].contiguous(), rd_all.reshape(-1, 3)[sel].contiguous()
+        tgt = torch.rand(96, 3, generator=gen)
+        tr = torch.rand(96, 32, generator=gen)
+        loss, _, _ = step(ro.cuda(), rd.cuda(), tgt.cuda(), t_rand=tr.cuda())
+        opt.step()
+        keys = list(cw.keys())
+        cwd = {k: p for k, p in zip(keys, cpu_params[:len(keys)])}
+        fwd = {k: p for k, p in zip(keys, cpu_params[len(keys):])}
+        l_ref, _, _, gc, gf = O.train_loss_and_grads(cwd, fwd, ro, rd, tgt, 32, 64, tr)
+        cpu_opt.zero_grad()
+        for k in keys:
+            cwd[k].grad, fwd[k].grad = gc[k], gf[k]
+        cpu_opt.step()
+        assert abs(float(loss) - float(l_ref)) <= 2e-5 * float(l_ref)
+    for k, p in coarse.named_parameters():
+        ref = cpu_params[list(cw.keys()).index(k)]
+        assert (p.detach().cpu() - ref.detach()).abs().max() <= 2e-5, k
