@@ -179,8 +179,8 @@ def main():
     weights = lego_weights()
     net = ops.pack_weights({k: v.to(dev) for k, v in weights.items()}, dev)
     # row band of this rank
-    rows = [H * r // world for r in range(world + 1)]
-    row0, n_rows = rows[rank], rows[rank + 1] - rows[rank]
+    from nerf_dbr_b200.host.parallel import row_band
+    row0, n_rows = row_band(rank, world, H)
     rgb = torch.empty(n_rows, W, 3, device=dev)
     depth = torch.empty(n_rows, W, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)

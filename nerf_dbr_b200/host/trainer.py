@@ -7,11 +7,11 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 
 from . import lib as L
 from . import ops
 from .model import NeRFModel
+from .parallel import allreduce_sum_
 
 
 class B200TrainStep:
@@ -40,12 +40,6 @@ class B200TrainStep:
         lf, rgb_f = ops.train_fwd_bwd(self.fine, rays_o, rays_d, target, self.n_fine, None, n_rays_global,
                                       self.near, self.far, self.mode)
         loss = lc + lf
-        if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in self.parameters()] + [loss.reshape(1)])
-            dist.all_reduce(flat)                # one 4.24 MB sum over NVLink
-            off = 0
-            for p in self.parameters():
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-            loss = flat[-1]
+        if allreduce:
+            loss = allreduce_sum_([p.grad for p in self.parameters()], extra=loss)   # one 4.24 MB sum over NVLink
         return loss, rgb_c, rgb_f
