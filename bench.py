@@ -20,6 +20,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line (the JSON): everything else any library prints to fd 1 (NCCL's version
+# banner, torchrun notices) is sent to stderr; emit() writes the result to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 W, H, S = 800, 600, 128
 N_VIEWS = 40
 FLOP_PER_SAMPLE = 1_055_744
@@ -144,7 +153,7 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -282,7 +291,7 @@ def main():
         n, dt, cores = cpu_baseline_sample(12.0)
         line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                 "sample": f"first {n} rays of view 0 at 800x600x128, 512-ray chunks ({dt:.1f} s)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
