@@ -28,9 +28,13 @@
 //     in shared memory (L0 and the skip part of L4).
 //   * The view direction enters colour layer 0 as an fp32 per-ray bias (W_dir . enc(d) + b),
 //     computed once per ray on CUDA cores: no per-sample direction encoding at all.
-//   * density head (256 FMAs/row) and the 128->3 colour output run in the epilogue from the fp32
-//     accumulators; compositing is a segmented warp scan (transmittance products) by the
-//     front/back warps, which also generate the next tile's rays, depths and encodings.
+//   * The density head rides in colour layer 0's GEMM as output column 128 (N = 144; bf16 like every
+//     other layer: < 0.01 dB against computing it in fp32, tools/emulate_bf16.py) instead of 256 CUDA-core
+//     FMAs per sample.  Colour layer 0's epilogue -- relu(acc + per-ray bias) . W_c1 -> sigmoid, sigma =
+//     relu(col 128 + b) -- belongs to the back warps, which read the accumulator straight from TMEM and
+//     then composite (segmented warp scan of transmittance products); the epilogue warps go from layer 7
+//     directly to the next tile's layer 0.  The front/back warps also generate the next tile's rays,
+//     depths and encodings.
 //
 // Warp roles (512 threads): 0 weight producer | 1 MMA issuer | 2 TMEM allocator | 4-11 epilogue
 // (lane quadrant = warp % 4, 64-column part of a half = (warp-4)/4) | 12-15 front (encode) /
@@ -57,13 +61,11 @@ constexpr int kMaxRaysPerTile = 8;      // S_pad >= 16
 
 // shared memory map (bytes from a 1024-aligned base)
 constexpr uint32_t SM_PE = 0;                              // 2 x [128 x 64] bf16 encoded-position tiles
-constexpr uint32_t SM_W = 32768;                           // kWStages x 32 KB weight stages
-constexpr uint32_t SM_BIAS = SM_W + kWStages * kStageBytes;    // [8][256] f32
-constexpr uint32_t SM_WSIG = SM_BIAS + 8192;               // [256] f32
-constexpr uint32_t SM_WC1 = SM_WSIG + 1024;                // [3][128] f32
+constexpr uint32_t SM_W = 32768;                           // kWStages weight stages (slot = largest stage, 36 KB)
+constexpr uint32_t SM_BIAS = SM_W + kWStages * kStageSlotBytes;    // [8][256] f32
+constexpr uint32_t SM_WC1 = SM_BIAS + 8192;                // [3][128] f32
 constexpr uint32_t SM_RAYB = SM_WC1 + 1536;                // [2][8][128] f32  per-ray colour-0 bias
-constexpr uint32_t SM_FIN = SM_RAYB + 8192;                // [2][128][8] f32  per-row head partials
-constexpr uint32_t SM_DE = SM_FIN + 8192;                  // [8][32] f32      direction encodings
+constexpr uint32_t SM_DE = SM_RAYB + 8192;                 // [8][32] f32      direction encodings
 constexpr uint32_t SM_SCR = SM_DE + 1024;                  // back-warp scratch (256 B)
 constexpr uint32_t SM_BAR = SM_SCR + 256;                  // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
@@ -73,8 +75,8 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kWStages, B_PEFULL = B_WEMPTY + kWStages, B_PEEMPTY = B_PEFULL + 2,
-       B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 2, B_FINFULL = B_AREADY + 4, B_FINEMPTY = B_FINFULL + 2,
-       B_ACCC0 = B_FINEMPTY + 2, B_COUNT = B_ACCC0 + 1 };
+       B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 2, B_ACCC0 = B_AREADY + 4, B_C0FREE = B_ACCC0 + 1,
+       B_COUNT = B_C0FREE + 1 };
 // Phase discipline (mbarrier parity waits are only sound while the producer is at most ONE phase ahead of
 // every waiter): acc_full[h] completes once per trunk layer 0..7 and each completion needs the previous
 // layer's epilogue; colour layer 0 has its own barrier because the NEXT tile's layer 0 follows it with no
@@ -247,20 +249,16 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pb, int r
 // back: sigmoid / relu heads, alpha, segmented transmittance scan, weighted sums, output
 template <int SRC>
 __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int row, float step,
-                               const float *__restrict__ wf, uint32_t bar_fin_empty)
+                               const float *__restrict__ wf, uint32_t bar_fin_empty, float sig_pre, const float (&ypre)[3])
 {
     const int lane = row & 31, warp = row >> 5;
-    const float4 *fin = reinterpret_cast<const float4 *>(sm + SM_FIN + fb * 4096 + row * 32);
-    float4 f0 = fin[0], f1 = fin[1];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_fin_empty);           // partials are in registers
+    (void)fb; (void)bar_fin_empty;
 
     RowInfo ri = row_info(a, tile, row);
-    float sigma = fmaxf(f0.x + f0.y + __ldg(wf + F_BSIG), 0.f);
+    float sigma = fmaxf(sig_pre + __ldg(wf + F_BSIG), 0.f);
     float col[3];
-    col[0] = 1.0f / (1.0f + expf(-(f0.z + f1.y + __ldg(wf + F_BC1 + 0))));
-    col[1] = 1.0f / (1.0f + expf(-(f0.w + f1.z + __ldg(wf + F_BC1 + 1))));
-    col[2] = 1.0f / (1.0f + expf(-(f1.x + f1.w + __ldg(wf + F_BC1 + 2))));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) col[c] = 1.0f / (1.0f + expf(-(ypre[c] + __ldg(wf + F_BC1 + c))));
     float alpha = 0.f, keep = 1.f, z = 0.f;
     if (ri.valid && a.n_samples > 1) {                  // S == 1 renders black in the reference (empty dists)
         float o[3], d[3];
@@ -354,9 +352,7 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
 // + bias, ReLU, bf16, and tcgen05.st of the 32 packed columns back over the first half of the
 // columns this warp has just read = one K-block of the next layer's A operand (K-major in TMEM).
 // kSigma (layer 7 only) also accumulates the density-head dot product from the fp32 values.
-template <bool kSigma>
-__device__ __forceinline__ void bias_relu_pack(const uint32_t (&x)[32], uint32_t *pk, uint32_t bias_addr,
-                                               uint32_t wsig_addr, float &sig)
+__device__ __forceinline__ void bias_relu_pack(const uint32_t (&x)[32], uint32_t *pk, uint32_t bias_addr)
 {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -367,27 +363,24 @@ __device__ __forceinline__ void bias_relu_pack(const uint32_t (&x)[32], uint32_t
         add2(x2, x3, b.z, b.w);
         pk[2 * i + 0] = relu_pack_bf16(x0, x1);
         pk[2 * i + 1] = relu_pack_bf16(x2, x3);
-        if (kSigma) {
-            const float4 w4 = ld_shared_f4(wsig_addr + 16 * i);
-            sig = fmaf(fmaxf(x0, 0.f), w4.x, sig); sig = fmaf(fmaxf(x1, 0.f), w4.y, sig);
-            sig = fmaf(fmaxf(x2, 0.f), w4.z, sig); sig = fmaf(fmaxf(x3, 0.f), w4.w, sig);
-        }
     }
 }
-template <bool kSigma>
-__device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t wsig_addr, float &sig)
+__device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane)
 {
     uint32_t xa[32], xb[32], pk[32];
     tmem_ld32(t_cols, xa);
     tmem_ld32(t_cols + 32, xb);
     tmem_ld_wait();
-    bias_relu_pack<kSigma>(xa, pk, bias_addr, wsig_addr, sig);
-    bias_relu_pack<kSigma>(xb, pk + 16, bias_addr + 128, wsig_addr + 128, sig);
+    bias_relu_pack(xa, pk, bias_addr);
+    bias_relu_pack(xb, pk + 16, bias_addr + 128);
     tmem_st32(t_cols, pk);
     tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_ready);
 }
 
-// colour layer 0 (N = 128; this warp: 64 columns): relu(acc + per-ray bias) . W_c1 -> 3 partial sums
+// 32 columns of colour layer 0: relu(acc + per-ray bias) . W_c1 -> 3 partial sums
 __device__ __forceinline__ void color_dot(const uint32_t (&x)[32], uint32_t rayb_addr, uint32_t wc1_addr,
                                           float &r0, float &r1, float &r2)
 {
@@ -407,16 +400,28 @@ __device__ __forceinline__ void color_dot(const uint32_t (&x)[32], uint32_t rayb
         r2 = fmaf(x0, w2.x, r2); r2 = fmaf(x1, w2.y, r2); r2 = fmaf(x2, w2.z, r2); r2 = fmaf(x3, w2.w, r2);
     }
 }
-__device__ __forceinline__ void epilogue_color(uint32_t t_cols, uint32_t rayb_addr, uint32_t wc1_addr,
-                                               float &r0, float &r1, float &r2)
+// back warps: this thread's row of colour layer 0's accumulator (128 columns) -> 3 colour pre-activations
+__device__ __forceinline__ void color_row(uint32_t t_row, uint32_t rayb_addr, uint32_t wc1_addr, uint32_t bar_c0free,
+                                          int lane, float &r0, float &r1, float &r2, float &sig_pre)
 {
     uint32_t xa[32], xb[32];
-    tmem_ld32(t_cols, xa);
-    tmem_ld32(t_cols + 32, xb);
-    tmem_ld_wait();
     r0 = r1 = r2 = 0.f;
+    const uint32_t sg = tmem_ld1(t_row + 128);              // density head: accumulator column 128
+    tmem_ld32(t_row, xa);
+    tmem_ld32(t_row + 32, xb);
+    tmem_ld_wait();
     color_dot(xa, rayb_addr, wc1_addr, r0, r1, r2);
+    tmem_ld32(t_row + 64, xa);
     color_dot(xb, rayb_addr + 128, wc1_addr + 128, r0, r1, r2);
+    tmem_ld32(t_row + 96, xb);
+    tmem_ld_wait();
+    // the accumulator is in registers: the next tile's layer 1 may overwrite it
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_c0free);
+    sig_pre = __uint_as_float(sg);
+    color_dot(xa, rayb_addr + 256, wc1_addr + 256, r0, r1, r2);
+    color_dot(xb, rayb_addr + 384, wc1_addr + 384, r0, r1, r2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -428,6 +433,7 @@ struct IssueCtx {
     uint64_t wdesc;         // smem descriptor of weight ring slot 0, chunk 0
     uint64_t pedesc;        // smem descriptor of this tile's encoded-position operand
     uint32_t pe_empty_bar;  // barrier released when layer 4 has consumed the encoded position
+    int tile;               // CTA-local tile index
     unsigned int *dbg;
     long long *trace;       // this tile's trace rows or nullptr
 };
@@ -437,17 +443,23 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
 {
     constexpr ChunkInfo c = kChunks.c[CI];
     constexpr int stage = CI / kStageChunks, slot = stage % kWStages;
-    constexpr uint32_t idesc = idesc_bf16(128, 128);
+    constexpr uint32_t idesc = c.layer == 8 ? idesc_bf16(128, kC0Rows) : idesc_bf16(128, 128);
+    constexpr uint32_t chunk_in_slot = (uint32_t)(chunk_offset(CI) - stage_offset(stage));
     constexpr bool last_of_layer = CI + 1 == kChunksPerTile || kChunks.c[CI + 1 < kChunksPerTile ? CI + 1 : CI].layer != c.layer;
     constexpr bool first_of_layer = CI == 0 || kChunks.c[CI > 0 ? CI - 1 : 0].layer != c.layer;
     if constexpr (CI % kStageChunks == 0)
         wait_bar(x.bars + 8u * (B_WFULL + slot), (stage / kWStages) & 1, x.dbg, 4);
     if constexpr ((c.flags & 4) != 0)      // a_ready[kb]: one phase per producing layer 0..7 (8 per tile: parity restarts)
         wait_bar(x.bars + 8u * (B_AREADY + c.asrc), (c.layer - 1) & 1, x.dbg, 3);
+    if constexpr (c.layer == 1 && first_of_layer) {
+        // layer 1 overwrites the region colour layer 0 of the PREVIOUS tile accumulated into: wait until the
+        // back warps have pulled it into registers
+        if (x.tile > 0) wait_bar(x.bars + 8u * B_C0FREE, (x.tile - 1) & 1, x.dbg, 10);
+    }
     tc_fence_after_sync();
     if (elect_one()) {
         const uint32_t d_tmem = x.region[c.layer & 1] + c.half * 128;
-        const uint64_t bdesc = x.wdesc + (uint64_t)((slot * kStageBytes + (CI % kStageChunks) * kChunkBytes) >> 4);
+        const uint64_t bdesc = x.wdesc + (uint64_t)((slot * kStageSlotBytes + chunk_in_slot) >> 4);
         if constexpr (c.asrc == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)          // 4 x (K = 16): +32 B inside the 128 B swizzle span
@@ -500,10 +512,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         for (int i = 0; i < kWStages; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
-            mbar_init(bar(B_FINFULL + i), 8); mbar_init(bar(B_FINEMPTY + i), 4);
         }
         for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACCFULL + i), 1);
         mbar_init(bar(B_ACCC0), 1);
+        mbar_init(bar(B_C0FREE), 4);
         for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), 4);
         fence_mbar_init();
     }
@@ -511,8 +523,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
     {   // small fp32 tables the epilogue reads as shared-memory broadcasts
         float *bias = reinterpret_cast<float *>(sm + SM_BIAS);
         for (int i = threadIdx.x; i < 8 * 256; i += kThreads) bias[i] = __ldg(wf + F_BIAS + i);
-        float *wsig = reinterpret_cast<float *>(sm + SM_WSIG);
-        for (int i = threadIdx.x; i < 256; i += kThreads) wsig[i] = __ldg(wf + F_WSIG + i);
         float *wc1 = reinterpret_cast<float *>(sm + SM_WC1);
         for (int i = threadIdx.x; i < 384; i += kThreads) wc1[i] = __ldg(wf + F_WC1 + i);
     }
@@ -530,9 +540,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                 for (int st = 0; st < kStagesPerTile; ++st, ++sg) {
                     const uint32_t slot = sg % kWStages, round = sg / kWStages;
                     if (round > 0) wait_bar(bar(B_WEMPTY + slot), (round - 1) & 1, a.dbg, 1);
-                    mbar_arrive_expect_tx(bar(B_WFULL + slot), kStageBytes);
-                    bulk_g2s(sm_base + SM_W + slot * kStageBytes, wb + (size_t)st * kStageBytes, kStageBytes,
-                             bar(B_WFULL + slot));
+                    mbar_arrive_expect_tx(bar(B_WFULL + slot), stage_bytes(st));
+                    bulk_g2s(sm_base + SM_W + slot * kStageSlotBytes, wb + stage_offset(st), stage_bytes(st), bar(B_WFULL + slot));
                 }
             }
         }
@@ -551,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             x.region[1] = tmem_base + (uint32_t)((t & 1) ^ 1) * 256;
             x.pedesc = smem_desc_sw128(sm_base + SM_PE + pb * 16384);
             x.pe_empty_bar = bar(B_PEEMPTY + pb);
+            x.tile = t;
             x.trace = (a.trace && blockIdx.x == 0 && t < kTraceTiles) ? a.trace + t * 72 : nullptr;
             issue_tile(x, std::make_integer_sequence<int, kChunksPerTile>{});
         }
@@ -560,49 +570,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         const int row = q * 32 + lane;
         uint32_t g = 0;
         for (int t = 0; t < my_tiles; ++t) {
-            const int pb = t & 1, fb = t & 1;
-            float *fin = reinterpret_cast<float *>(sm + SM_FIN + fb * 4096 + row * 32);
             long long *tr = (a.trace && blockIdx.x == 0 && t < kTraceTiles && ew == 0 && lane == 0) ? a.trace + t * 72 : nullptr;
-            for (int layer = 0; layer < 9; ++layer, ++g) {
+            for (int layer = 0; layer < 8; ++layer, ++g) {
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
-                if (layer < 8) {
-                    float sig = 0.f;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        wait_bar(bar(B_ACCFULL + hh), layer & 1, a.dbg, 5);      // 8 phases per tile: parity = layer
-                        tc_fence_after_sync();
-                        if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
-                        const uint32_t n0 = hh * 128 + 64 * w2;
-                        if (layer == 7)
-                            epilogue_half<true>(t_lane + hh * 128, sm_base + SM_BIAS + (7 * 256 + n0) * 4,
-                                                sm_base + SM_WSIG + n0 * 4, sig);
-                        else
-                            epilogue_half<false>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + n0) * 4, 0, sig);
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
-                        if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
-                    }
-                    if (layer == 7) {
-                        if (t >= 2) wait_bar(bar(B_FINEMPTY + fb), ((t >> 1) - 1) & 1, a.dbg, 6);
-                        fin[w2] = sig;
-                    }
-                } else {
-                    wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 7);     // orders the per-ray bias writes
-                    wait_bar(bar(B_ACCC0), t & 1, a.dbg, 5);
+                for (int hh = 0; hh < 2; ++hh) {
+                    wait_bar(bar(B_ACCFULL + hh), layer & 1, a.dbg, 5);      // 8 phases per tile: parity = layer
                     tc_fence_after_sync();
-                    if (tr) tr[layer * 8 + 3] = clock64();
-                    const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
-                    const uint32_t rayb = sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512 + w2 * 256;
-                    float r0, r1, r2;
-                    epilogue_color(t_lane, rayb, sm_base + SM_WC1 + w2 * 256, r0, r1, r2);
-                    fin[2 + 3 * w2 + 0] = r0; fin[2 + 3 * w2 + 1] = r1; fin[2 + 3 * w2 + 2] = r2;
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(B_FINFULL + fb));
+                    if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
+                    epilogue_half(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
+                                  bar(B_AREADY + 2 * hh + w2), lane);
+                    if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();
             }
+            ++g;                                    // colour layer 0 (the back warps' epilogue) takes a region turn too
         }
     } else if (warp >= 12) {
         // ================================ front / back =======================================
@@ -619,9 +601,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         if (my_tiles > 0) produce(0);
         for (int t = 0; t < my_tiles; ++t) {
             if (t + 1 < my_tiles) produce(t + 1);
-            const int fb = t & 1;
-            wait_bar(bar(B_FINFULL + fb), (t >> 1) & 1, a.dbg, 9);
-            composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, bar(B_FINEMPTY + fb));
+            const int fb = t & 1, pb = t & 1;
+            // colour layer 0's epilogue: this thread's accumulator row straight from TMEM
+            wait_bar(bar(B_ACCC0), t & 1, a.dbg, 11);
+            tc_fence_after_sync();
+            const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp - 12) * 32) << 16) + (uint32_t)(t & 1) * 256;
+            float ypre[3], sig_pre;
+            color_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
+                      bar(B_C0FREE), lane, ypre[0], ypre[1], ypre[2], sig_pre);
+            composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, 0, sig_pre, ypre);
         }
     }
 

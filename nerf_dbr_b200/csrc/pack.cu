@@ -4,7 +4,8 @@
 
 namespace nerfb200 {
 
-struct ChunkSrc { const float *w; int ld; int n0; int k0; int k_valid; };   // rows n0.., columns k0..k0+63
+struct ChunkSrc { const float *w; int ld; int n0; int k0; int k_valid; int rows; const float *extra; };
+// rows n0.. (n < rows), columns k0..k0+63; `extra` = one more row (the density head inside colour layer 0's chunks)
 
 __constant__ ChunkTable kPackTable = make_chunk_table();
 
@@ -13,11 +14,11 @@ __device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int 
 {
     const ChunkInfo c = kPackTable.c[ci];
     const int n0 = 128 * c.half;
-    if (c.layer == 0) return {p.layer_w[0], 63, n0, 0, 63};
-    if (c.layer == 8) return {p.color0_w, 283, n0, 64 * c.asrc, 64};
-    if (c.layer == 4) return c.asrc == 4 ? ChunkSrc{p.layer_w[4], 319, n0, 256, 63}
-                                         : ChunkSrc{p.layer_w[4], 319, n0, 64 * c.asrc, 64};
-    return {p.layer_w[c.layer], 256, n0, 64 * c.asrc, 64};
+    if (c.layer == 0) return {p.layer_w[0], 63, n0, 0, 63, 128, nullptr};
+    if (c.layer == 8) return {p.color0_w, 283, n0, 64 * c.asrc, 64, 128, p.density_w + 64 * c.asrc};
+    if (c.layer == 4) return c.asrc == 4 ? ChunkSrc{p.layer_w[4], 319, n0, 256, 63, 128, nullptr}
+                                         : ChunkSrc{p.layer_w[4], 319, n0, 64 * c.asrc, 64, 128, nullptr};
+    return {p.layer_w[c.layer], 256, n0, 64 * c.asrc, 64, 128, nullptr};
 }
 
 __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ packed)
@@ -54,19 +55,29 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
     }
 
     // ---- bf16 region: one 16-byte unit (8 consecutive k of one row) per thread-iteration ----
-    const size_t units = (size_t)kChunksPerTile * 128 * 8;
+    constexpr size_t units_trunk = (size_t)(kChunksPerTile - kChunksC0) * 128 * 8;
+    constexpr size_t units = units_trunk + (size_t)kChunksC0 * kC0Rows * 8;
     for (size_t uidx = tid; uidx < units; uidx += nth) {
-        const int ci = (int)(uidx / 1024), n = (int)((uidx % 1024) / 8), unit = (int)(uidx % 8);
+        int ci, n, unit;
+        if (uidx < units_trunk) { ci = (int)(uidx / 1024); n = (int)((uidx % 1024) / 8); unit = (int)(uidx % 8); }
+        else {
+            size_t r = uidx - units_trunk;
+            ci = (kChunksPerTile - kChunksC0) + (int)(r / (kC0Rows * 8)); n = (int)((r % (kC0Rows * 8)) / 8); unit = (int)(r % 8);
+        }
         const ChunkSrc src = chunk_source(p, ci);
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int k = unit * 8 + j;
-            float w = k < src.k_valid ? src.w[(size_t)(src.n0 + n) * src.ld + src.k0 + k] : 0.f;
+            float w = 0.f;
+            if (k < src.k_valid) {
+                if (n < src.rows) w = src.w[(size_t)(src.n0 + n) * src.ld + src.k0 + k];
+                else if (n == src.rows && src.extra) w = src.extra[k];
+            }
             hi[j] = __float2bfloat16_rn(w);
             lo[j] = __float2bfloat16_rn(w - __bfloat162float(hi[j]));
         }
-        size_t off = (size_t)ci * kChunkBytes + swz128((uint32_t)n, (uint32_t)unit * 8);
+        size_t off = chunk_offset(ci) + swz128((uint32_t)n, (uint32_t)unit * 8);
         *reinterpret_cast<uint4 *>(packed + B_OFFSET + off) = *reinterpret_cast<const uint4 *>(hi);
         *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
     }

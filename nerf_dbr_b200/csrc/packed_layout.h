@@ -54,12 +54,27 @@ __host__ __device__ constexpr size_t f_wt(int layer) { return F_WT + (size_t)(la
 //   * half 0 completes after the 5th chunk, so its epilogue (bias, ReLU, bf16, write-back) is done
 //     before the layer ends; half 1's epilogue overlaps the next layer's first three chunks.
 //   layer 4 adds an encoded-position chunk per half (no dependency); layer 0 is those alone;
-//   colour layer 0 has one half.
+//   colour layer 0 has one half of N = 144: rows 0..127 are colour layer 0's hidden-input weights,
+//   row 128 is the DENSITY HEAD (its output lands in accumulator column 128 -- 256 FMAs per sample
+//   that would otherwise run on CUDA cores), rows 129..143 are zero padding (N must be a multiple of 16).
 constexpr int kChunkBytes = 128 * 128;                        // [128 x 64] bf16
+constexpr int kC0Rows = 144;
+constexpr int kChunkBytesC0 = kC0Rows * 128;                  // [144 x 64] bf16
 constexpr int kChunksPerTile = 64;
+constexpr int kChunksC0 = 4;                                  // the last four chunks
 constexpr int kStageChunks = 2;
-constexpr int kStageBytes = kStageChunks * kChunkBytes;       // 32 KB
+constexpr int kStageBytes = kStageChunks * kChunkBytes;       // 32 KB (trunk stages)
+constexpr int kStageBytesC0 = kStageChunks * kChunkBytesC0;   // 36 KB (the two colour-layer-0 stages)
 constexpr int kStagesPerTile = kChunksPerTile / kStageChunks; // 32
+constexpr int kStagesC0 = kChunksC0 / kStageChunks;           // 2
+constexpr int kStageSlotBytes = kStageBytesC0;                // ring slot size
+__host__ __device__ constexpr size_t chunk_offset(int ci)
+{
+    return ci < kChunksPerTile - kChunksC0 ? (size_t)ci * kChunkBytes
+                                           : (size_t)(kChunksPerTile - kChunksC0) * kChunkBytes + (size_t)(ci - (kChunksPerTile - kChunksC0)) * kChunkBytesC0;
+}
+__host__ __device__ constexpr size_t stage_offset(int st) { return chunk_offset(st * kStageChunks); }
+__host__ __device__ constexpr uint32_t stage_bytes(int st) { return st < kStagesPerTile - kStagesC0 ? kStageBytes : kStageBytesC0; }
 
 struct ChunkInfo {
     uint8_t layer;   // 0..7 trunk, 8 = colour layer 0
@@ -111,7 +126,7 @@ constexpr ChunkTable make_chunk_table()
 static_assert(make_chunk_table().c[kChunksPerTile - 1].layer == 8, "chunk table must fill exactly 64 entries");
 
 constexpr size_t B_OFFSET = ((F_END * 4 + 1023) / 1024) * 1024;   // byte offset of the bf16 region
-constexpr size_t B_BYTES = (size_t)kChunksPerTile * kChunkBytes;  // 1 MiB
+constexpr size_t B_BYTES = chunk_offset(kChunksPerTile);            // ~1 MiB
 // low-order bf16 stream for a split-precision mode follows (same layout)
 constexpr size_t B_LO_OFFSET = B_OFFSET + B_BYTES;
 constexpr size_t PACKED_BYTES = B_LO_OFFSET + B_BYTES;

@@ -38,9 +38,9 @@ def mlp_bf16(w, pts, rays_d_per_sample):
         else:
             acc = h @ W.T
         x = torch.relu(acc + w[f"layers.{i}.bias"])
-        if i == 7:
-            sigma = torch.relu(x @ w["density_head.weight"].T + w["density_head.bias"])
         h = bf(x)
+    # the density head is column 128 of colour layer 0's GEMM: bf16 h7 x bf16 w_sigma, fp32 accumulate
+    sigma = torch.relu(h @ bf(w["density_head.weight"]).T + w["density_head.bias"])
     de = O.encode(rays_d_per_sample, 4)
     Wc = w["color_layers.0.weight"]
     bias = de @ Wc[:, 256:].T + w["color_layers.0.bias"]
