@@ -48,7 +48,10 @@ enum {
 /* Arithmetic of the MLP contraction. */
 enum {
     NERF_B200_FP32 = 0,   /* fp32 FFMA on CUDA cores: the <=1e-4 max-abs parity mode */
-    NERF_B200_BF16 = 1    /* bf16 operands, fp32 accumulate in TMEM (tcgen05): the throughput mode */
+    NERF_B200_BF16 = 1,   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): the throughput mode */
+    NERF_B200_BF16X3 = 2  /* tensor cores with every operand split into bf16 (hi, lo) and three MMAs per product
+                             (hi*hi + hi*lo + lo*hi): fp32-class accuracy (max-abs ~1e-5), ~1/3 of the BF16 rate.
+                             render_image / render_rays only */
 };
 
 /* The 22 parameter tensors of one NeRFModel (reference src/models/nerf.py:72-90), as

@@ -5,8 +5,8 @@ namespace nerfb200 {
 int simt_query(const void *, const float *, const float *, long long, float *, float *, cudaStream_t);
 int simt_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, cudaStream_t);
 int simt_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, float *, float *, float *, cudaStream_t);
-int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, unsigned int *, cudaStream_t);
-int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, float *, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, bool, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, bool, float *, float *, float *, unsigned int *, cudaStream_t);
 }
 using namespace nerfb200;
 
@@ -39,9 +39,9 @@ int nerf_b200_render_image(const void *packed, const float *c2w_host, int width,
     if (mode == NERF_B200_FP32)
         return simt_render_pose(packed, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows,
                                 rgb_out, depth_out, (cudaStream_t)stream);
-    if (mode == NERF_B200_BF16)
+    if (mode == NERF_B200_BF16 || mode == NERF_B200_BF16X3)
         return tc_render_pose(packed, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows,
-                              rgb_out, depth_out, g_watchdog, (cudaStream_t)stream);
+                              mode == NERF_B200_BF16X3, rgb_out, depth_out, g_watchdog, (cudaStream_t)stream);
     return NERF_B200_EINVAL;
 }
 
@@ -55,9 +55,9 @@ int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *
     if (mode == NERF_B200_FP32)
         return simt_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, rgb_out,
                                 depth_out, acc_out, (cudaStream_t)stream);
-    if (mode == NERF_B200_BF16)
-        return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, rgb_out,
-                              depth_out, acc_out, g_watchdog, (cudaStream_t)stream);
+    if (mode == NERF_B200_BF16 || mode == NERF_B200_BF16X3)
+        return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, mode == NERF_B200_BF16X3,
+                              rgb_out, depth_out, acc_out, g_watchdog, (cudaStream_t)stream);
     return NERF_B200_EINVAL;
 }
 

@@ -55,14 +55,29 @@ using namespace ptx;
 
 constexpr int kThreads = 512;
 constexpr int kTileM = 128;
-constexpr int kWStages = 4;
-static_assert(kStagesPerTile % kWStages == 0, "ring slots and barrier parities are compile-time per tile");
 constexpr int kMaxRaysPerTile = 8;      // S_pad >= 16
 
+// Two instantiations share one shared-memory map:
+//   SPLIT = false  bf16 operands; 4 weight slots of 36 KB; two single-plane encoded-position buffers
+//   SPLIT = true   every operand is a bf16 (hi, lo) pair and every product three MMAs
+//                  (hi*hi + hi*lo + lo*hi): fp32-class accuracy on the tensor cores (max-abs ~1e-5 against
+//                  the fp32 reference).  2 weight slots of 72 KB (hi stage | lo stage), one two-plane
+//                  encoded-position buffer; activations keep their lo halves in the 32 TMEM columns per
+//                  K-block that the bf16 mode leaves unused.
+template <bool SPLIT>
+struct Cfg {
+    static constexpr int kWSlots = SPLIT ? 2 : 4;
+    static constexpr uint32_t kSlotBytes = (SPLIT ? 2u : 1u) * kStageSlotBytes;
+    static constexpr int kPeBufs = SPLIT ? 1 : 2;
+    static constexpr int kMmaPerStep = SPLIT ? 3 : 1;
+};
+static_assert(kStagesPerTile % 4 == 0, "ring slots and barrier parities are compile-time per tile");
+constexpr int kMaxWSlots = 4;
+
 // shared memory map (bytes from a 1024-aligned base)
-constexpr uint32_t SM_PE = 0;                              // 2 x [128 x 64] bf16 encoded-position tiles
-constexpr uint32_t SM_W = 32768;                           // kWStages weight stages (slot = largest stage, 36 KB)
-constexpr uint32_t SM_BIAS = SM_W + kWStages * kStageSlotBytes;    // [8][256] f32
+constexpr uint32_t SM_PE = 0;                              // 32 KB: 2 x [128 x 64] bf16, or (hi, lo) planes of one tile
+constexpr uint32_t SM_W = 32768;                           // 144 KB of weight stages
+constexpr uint32_t SM_BIAS = SM_W + 4 * kStageSlotBytes;   // [8][256] f32
 constexpr uint32_t SM_WC1 = SM_BIAS + 8192;                // [3][128] f32
 constexpr uint32_t SM_RAYB = SM_WC1 + 1536;                // [2][8][128] f32  per-ray colour-0 bias
 constexpr uint32_t SM_DE = SM_RAYB + 8192;                 // [8][32] f32      direction encodings
@@ -74,7 +89,7 @@ constexpr uint32_t kSmemBytes = SM_TOTAL + 1024;           // + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kWStages, B_PEFULL = B_WEMPTY + kWStages, B_PEEMPTY = B_PEFULL + 2,
+enum { B_WFULL = 0, B_WEMPTY = B_WFULL + kMaxWSlots, B_PEFULL = B_WEMPTY + kMaxWSlots, B_PEEMPTY = B_PEFULL + 2,
        B_ACCFULL = B_PEEMPTY + 2, B_AREADY = B_ACCFULL + 2, B_ACCC0 = B_AREADY + 4, B_C0FREE = B_ACCC0 + 1,
        B_COUNT = B_C0FREE + 1 };
 // Phase discipline (mbarrier parity waits are only sound while the producer is at most ONE phase ahead of
@@ -178,8 +193,10 @@ __device__ __forceinline__ void sincos_phase(uint32_t phase, float &s, float &c)
 
 // ------------------------------------------------------------------------------------------
 // front: rays, depths, points, encoded-position tile (bf16, swizzled) and per-ray colour bias
-template <int SRC>
-__device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pb, int row, float step,
+__device__ __forceinline__ float bf16_hi(float v) { return __uint_as_float(__float_as_uint(__bfloat162float(__float2bfloat16_rn(v)))); }
+
+template <int SRC, bool SPLIT>
+__device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, int rb_buf, int row, float step,
                              const float *__restrict__ wf)
 {
     RowInfo ri = row_info(a, tile, row);
@@ -207,12 +224,21 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pb, int r
                 feat[3 + 6 * k + 3 + c] = cs;
             }
     }
-    const uint32_t pe_row = smem_u32(sm + SM_PE + pb * 16384 + row * 128);
+    const uint32_t pe_row = smem_u32(sm + SM_PE + pe_buf * 16384 + row * 128);
 #pragma unroll
     for (int u = 0; u < 8; ++u)
         st_shared_v4(pe_row + ((u ^ (row & 7)) << 4),
                      pack_bf16(feat[8 * u + 0], feat[8 * u + 1]), pack_bf16(feat[8 * u + 2], feat[8 * u + 3]),
                      pack_bf16(feat[8 * u + 4], feat[8 * u + 5]), pack_bf16(feat[8 * u + 6], feat[8 * u + 7]));
+    if (SPLIT) {                                           // low-order plane: feat - bf16(feat)
+#pragma unroll
+        for (int f = 0; f < 64; ++f) feat[f] -= bf16_hi(feat[f]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            st_shared_v4(pe_row + 16384 + ((u ^ (row & 7)) << 4),
+                         pack_bf16(feat[8 * u + 0], feat[8 * u + 1]), pack_bf16(feat[8 * u + 2], feat[8 * u + 3]),
+                         pack_bf16(feat[8 * u + 4], feat[8 * u + 5]), pack_bf16(feat[8 * u + 6], feat[8 * u + 7]));
+    }
 
     // direction encodings of the tile's rays: thread (q*32 + f) -> feature f of ray q (fp32, full-range sinf/cosf)
     const int rpt = a.tiles_per_ray == 1 ? (kTileM >> a.s_pad_log2) : 1;
@@ -235,7 +261,7 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pb, int r
         }
     }
     named_bar_sync(1, 128);
-    float *rayb = reinterpret_cast<float *>(sm + SM_RAYB) + pb * (kMaxRaysPerTile * 128);
+    float *rayb = reinterpret_cast<float *>(sm + SM_RAYB) + rb_buf * (kMaxRaysPerTile * 128);
     for (int q = 0; q < rpt; ++q) {
         float acc = __ldg(wf + F_BC0 + row);
 #pragma unroll
@@ -365,15 +391,46 @@ __device__ __forceinline__ void bias_relu_pack(const uint32_t (&x)[32], uint32_t
         pk[2 * i + 1] = relu_pack_bf16(x2, x3);
     }
 }
+// split precision: hi = bf16(relu(x + b)), lo = bf16(relu(x + b) - hi), 32 columns -> 16 + 16 packed columns
+__device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], uint32_t *hi, uint32_t *lo, uint32_t bias_addr)
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 b = ld_shared_f4(bias_addr + 16 * i);
+        float v[4] = {__uint_as_float(x[4 * i + 0]), __uint_as_float(x[4 * i + 1]), __uint_as_float(x[4 * i + 2]), __uint_as_float(x[4 * i + 3])};
+        add2(v[0], v[1], b.x, b.y);
+        add2(v[2], v[3], b.z, b.w);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float a0 = fmaxf(v[2 * j], 0.f), a1 = fmaxf(v[2 * j + 1], 0.f);
+            const uint32_t h = pack_bf16(a0, a1);
+            hi[2 * i + j] = h;
+            lo[2 * i + j] = pack_bf16(a0 - __uint_as_float(h << 16), a1 - __uint_as_float(h & 0xffff0000u));
+        }
+    }
+}
+
+template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane)
 {
-    uint32_t xa[32], xb[32], pk[32];
+    uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
     tmem_ld32(t_cols + 32, xb);
     tmem_ld_wait();
-    bias_relu_pack(xa, pk, bias_addr);
-    bias_relu_pack(xb, pk + 16, bias_addr + 128);
-    tmem_st32(t_cols, pk);
+    if (!SPLIT) {
+        uint32_t pk[32];
+        bias_relu_pack(xa, pk, bias_addr);
+        bias_relu_pack(xb, pk + 16, bias_addr + 128);
+        tmem_st32(t_cols, pk);                   // K-block: 64 bf16 in columns [0, 32) of this warp's range
+    } else {
+        uint32_t hi[16], lo[16];                 // hi halves in columns [0, 32), lo halves in [32, 64)
+        bias_relu_pack_split(xa, hi, lo, bias_addr);
+        tmem_st16(t_cols, hi);
+        tmem_st16(t_cols + 32, lo);
+        bias_relu_pack_split(xb, hi, lo, bias_addr + 128);
+        tmem_st16(t_cols + 16, hi);
+        tmem_st16(t_cols + 48, lo);
+    }
     tmem_st_wait();
     tc_fence_before_sync();
     __syncwarp();
@@ -431,24 +488,25 @@ struct IssueCtx {
     uint32_t bars;          // shared address of barrier 0
     uint32_t region[2];     // TMEM base of the accumulator region of even / odd layers of this tile
     uint64_t wdesc;         // smem descriptor of weight ring slot 0, chunk 0
-    uint64_t pedesc;        // smem descriptor of this tile's encoded-position operand
+    uint64_t pedesc;        // smem descriptor of this tile's encoded-position operand (hi plane)
     uint32_t pe_empty_bar;  // barrier released when layer 4 has consumed the encoded position
     int tile;               // CTA-local tile index
     unsigned int *dbg;
     long long *trace;       // this tile's trace rows or nullptr
 };
 
-template <int CI>
+template <int CI, bool SPLIT>
 __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
 {
+    using C = Cfg<SPLIT>;
     constexpr ChunkInfo c = kChunks.c[CI];
-    constexpr int stage = CI / kStageChunks, slot = stage % kWStages;
+    constexpr int stage = CI / kStageChunks, slot = stage % C::kWSlots;
     constexpr uint32_t idesc = c.layer == 8 ? idesc_bf16(128, kC0Rows) : idesc_bf16(128, 128);
     constexpr uint32_t chunk_in_slot = (uint32_t)(chunk_offset(CI) - stage_offset(stage));
     constexpr bool last_of_layer = CI + 1 == kChunksPerTile || kChunks.c[CI + 1 < kChunksPerTile ? CI + 1 : CI].layer != c.layer;
     constexpr bool first_of_layer = CI == 0 || kChunks.c[CI > 0 ? CI - 1 : 0].layer != c.layer;
     if constexpr (CI % kStageChunks == 0)
-        wait_bar(x.bars + 8u * (B_WFULL + slot), (stage / kWStages) & 1, x.dbg, 4);
+        wait_bar(x.bars + 8u * (B_WFULL + slot), (stage / C::kWSlots) & 1, x.dbg, 4);
     if constexpr ((c.flags & 4) != 0)      // a_ready[kb]: one phase per producing layer 0..7 (8 per tile: parity restarts)
         wait_bar(x.bars + 8u * (B_AREADY + c.asrc), (c.layer - 1) & 1, x.dbg, 3);
     if constexpr (c.layer == 1 && first_of_layer) {
@@ -459,18 +517,29 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
     tc_fence_after_sync();
     if (elect_one()) {
         const uint32_t d_tmem = x.region[c.layer & 1] + c.half * 128;
-        const uint64_t bdesc = x.wdesc + (uint64_t)((slot * kStageSlotBytes + chunk_in_slot) >> 4);
+        const uint64_t bdesc = x.wdesc + (uint64_t)((slot * C::kSlotBytes + chunk_in_slot) >> 4);
+        constexpr uint64_t kLoW = kStageSlotBytes >> 4;      // lo weight stage sits behind the hi stage in the slot
         if constexpr (c.asrc == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)          // 4 x (K = 16): +32 B inside the 128 B swizzle span
+            for (int k = 0; k < 4; ++k) {        // 4 x (K = 16): +32 B inside the 128 B swizzle span
                 mma_bf16_ss(d_tmem, x.pedesc + 2 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
+                if constexpr (SPLIT) {
+                    mma_bf16_ss(d_tmem, x.pedesc + 2 * k, bdesc + kLoW + 2 * k, idesc, true);             // hi * lo
+                    mma_bf16_ss(d_tmem, x.pedesc + (16384 >> 4) + 2 * k, bdesc + 2 * k, idesc, true);     // lo * hi
+                }
+            }
         } else {
             // A = K-block `asrc` of the previous layer: bf16 pairs written in place over the other
-            // region's accumulator columns [64 asrc, 64 asrc + 32)
+            // region's accumulator columns [64 asrc, 64 asrc + 32) (SPLIT: lo halves in [+32, +64))
             const uint32_t a_tmem = x.region[(c.layer & 1) ^ 1] + c.asrc * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
                 mma_bf16_ts(d_tmem, a_tmem + 8 * k, bdesc + 2 * k, idesc, !((c.flags & 1) && k == 0));
+                if constexpr (SPLIT) {
+                    mma_bf16_ts(d_tmem, a_tmem + 8 * k, bdesc + kLoW + 2 * k, idesc, true);
+                    mma_bf16_ts(d_tmem, a_tmem + 32 + 8 * k, bdesc + 2 * k, idesc, true);
+                }
+            }
         }
         if constexpr (first_of_layer) { if (x.trace) x.trace[c.layer * 8 + 0] = clock64(); }
         if constexpr ((c.flags & 2) != 0) {
@@ -482,16 +551,17 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
     }
     __syncwarp();
 }
-template <int... CI>
+template <bool SPLIT, int... CI>
 __device__ __forceinline__ void issue_tile(const IssueCtx &x, std::integer_sequence<int, CI...>)
 {
-    (issue_chunk<CI>(x), ...);
+    (issue_chunk<CI, SPLIT>(x), ...);
 }
 
 // ------------------------------------------------------------------------------------------
-template <int SRC>
+template <int SRC, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 {
+    using C = Cfg<SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array, so the compiler keeps the
     // shared address space (LDS/STS instead of generic LD/ST)
@@ -502,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
     auto bar = [&](int i) { return bars + 8u * i; };
     const float *wf = reinterpret_cast<const float *>(a.packed);
     const unsigned char *wb = a.packed + B_OFFSET;
+    const unsigned char *wb_lo = a.packed + B_LO_OFFSET;
 
     const int tile_begin = blockIdx.x * a.tiles_per_cta;
     const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_cta);
@@ -509,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 
     // ---- one-time setup -------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+        for (int i = 0; i < C::kWSlots; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
         }
@@ -538,10 +609,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             uint32_t sg = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 for (int st = 0; st < kStagesPerTile; ++st, ++sg) {
-                    const uint32_t slot = sg % kWStages, round = sg / kWStages;
+                    const uint32_t slot = sg % C::kWSlots, round = sg / C::kWSlots;
                     if (round > 0) wait_bar(bar(B_WEMPTY + slot), (round - 1) & 1, a.dbg, 1);
-                    mbar_arrive_expect_tx(bar(B_WFULL + slot), stage_bytes(st));
-                    bulk_g2s(sm_base + SM_W + slot * kStageSlotBytes, wb + stage_offset(st), stage_bytes(st), bar(B_WFULL + slot));
+                    const uint32_t bytes = stage_bytes(st), dst = sm_base + SM_W + slot * C::kSlotBytes;
+                    mbar_arrive_expect_tx(bar(B_WFULL + slot), SPLIT ? 2 * bytes : bytes);
+                    bulk_g2s(dst, wb + stage_offset(st), bytes, bar(B_WFULL + slot));
+                    if (SPLIT) bulk_g2s(dst + kStageSlotBytes, wb_lo + stage_offset(st), bytes, bar(B_WFULL + slot));
                 }
             }
         }
@@ -553,16 +626,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         x.wdesc = smem_desc_sw128(sm_base + SM_W);
         x.dbg = a.dbg;
         for (int t = 0; t < my_tiles; ++t) {
-            const int pb = t & 1;
-            wait_bar(bar(B_PEFULL + pb), (t >> 1) & 1, a.dbg, 2);
+            // encoded-position buffers: two alternate (bf16) or one is reused every tile (split)
+            const int pb = SPLIT ? 0 : (t & 1), pe_use = SPLIT ? t : (t >> 1);
+            wait_bar(bar(B_PEFULL + pb), pe_use & 1, a.dbg, 2);
             // nine layers per tile: the region parity of layer l of tile t is (t + l) & 1
             x.region[0] = tmem_base + (uint32_t)(t & 1) * 256;
             x.region[1] = tmem_base + (uint32_t)((t & 1) ^ 1) * 256;
-            x.pedesc = smem_desc_sw128(sm_base + SM_PE + pb * 16384);
+            x.pedesc = smem_desc_sw128(sm_base + SM_PE + (SPLIT ? 0 : pb * 16384));
             x.pe_empty_bar = bar(B_PEEMPTY + pb);
             x.tile = t;
             x.trace = (a.trace && blockIdx.x == 0 && t < kTraceTiles) ? a.trace + t * 72 : nullptr;
-            issue_tile(x, std::make_integer_sequence<int, kChunksPerTile>{});
+            issue_tile<SPLIT>(x, std::make_integer_sequence<int, kChunksPerTile>{});
         }
     } else if (warp >= 4 && warp < 12) {
         // ================================ epilogue ===========================================
@@ -578,8 +652,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     wait_bar(bar(B_ACCFULL + hh), layer & 1, a.dbg, 5);      // 8 phases per tile: parity = layer
                     tc_fence_after_sync();
                     if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
-                    epilogue_half(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                  bar(B_AREADY + 2 * hh + w2), lane);
+                    epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
+                                         bar(B_AREADY + 2 * hh + w2), lane);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();
@@ -591,9 +665,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         const int row = (warp - 12) * 32 + lane;
         const float step = linspace_step(a.n_samples);
         auto produce = [&](int t) {
-            const int pb = t & 1;
-            if (t >= 2) wait_bar(bar(B_PEEMPTY + pb), ((t >> 1) - 1) & 1, a.dbg, 8);
-            produce_tile<SRC>(a, sm, tile_begin + t, pb, row, step, wf);
+            const int pb = SPLIT ? 0 : (t & 1), pe_use = SPLIT ? t : (t >> 1);
+            if (pe_use >= 1) wait_bar(bar(B_PEEMPTY + pb), (pe_use - 1) & 1, a.dbg, 8);
+            produce_tile<SRC, SPLIT>(a, sm, tile_begin + t, pb, t & 1, row, step, wf);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_PEFULL + pb));
@@ -601,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         if (my_tiles > 0) produce(0);
         for (int t = 0; t < my_tiles; ++t) {
             if (t + 1 < my_tiles) produce(t + 1);
-            const int fb = t & 1, pb = t & 1;
+            const int fb = t & 1, pb = t & 1;           // per-ray bias buffers always alternate
             // colour layer 0's epilogue: this thread's accumulator row straight from TMEM
             wait_bar(bar(B_ACCC0), t & 1, a.dbg, 11);
             tc_fence_after_sync();
@@ -648,14 +722,14 @@ static int plan(Args &a)
     return (a.n_tiles + per - 1) / per;               // grid
 }
 
-template <int SRC>
+template <int SRC, bool SPLIT>
 static int launch(Args &a, cudaStream_t stream)
 {
     int grid = plan(a);
     if (grid < 0) return grid;
-    cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    fused_render_kernel<SRC><<<grid, kThreads, kSmemBytes, stream>>>(a);
+    fused_render_kernel<SRC, SPLIT><<<grid, kThreads, kSmemBytes, stream>>>(a);
     return launch_status();
 }
 
@@ -664,7 +738,7 @@ static int launch(Args &a, cudaStream_t stream)
 long long *g_tc_trace = nullptr;     // set through nerf_b200_set_trace_buffer (tools/tc_trace.py)
 
 int tc_render_pose(const void *packed, const float *c2w, int width, int height, float focal, float near,
-                   float far, int n_samples, int row0, int n_rows, float *rgb_out, float *depth_out,
+                   float far, int n_samples, int row0, int n_rows, bool split, float *rgb_out, float *depth_out,
                    unsigned int *dbg, cudaStream_t stream)
 {
     tc::Args a = {};
@@ -676,11 +750,11 @@ int tc_render_pose(const void *packed, const float *c2w, int width, int height, 
     a.n_rays = n_rows * width; a.n_samples = n_samples;
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = nullptr; a.dbg = dbg;
-    return tc::launch<tc::SRC_POSE>(a, stream);
+    return split ? tc::launch<tc::SRC_POSE, true>(a, stream) : tc::launch<tc::SRC_POSE, false>(a, stream);
 }
 
 int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples,
-                   float near, float far, const float *t_rand, float *rgb_out, float *depth_out,
+                   float near, float far, const float *t_rand, bool split, float *rgb_out, float *depth_out,
                    float *acc_out, unsigned int *dbg, cudaStream_t stream)
 {
     tc::Args a = {};
@@ -689,7 +763,7 @@ int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d,
     a.n_rays = n_rays; a.n_samples = n_samples;
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
-    return tc::launch<tc::SRC_RAYS>(a, stream);
+    return split ? tc::launch<tc::SRC_RAYS, true>(a, stream) : tc::launch<tc::SRC_RAYS, false>(a, stream);
 }
 
 }  // namespace nerfb200

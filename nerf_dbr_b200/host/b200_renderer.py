@@ -22,17 +22,19 @@ except Exception:  # standalone
 
 
 class B200Renderer(_Base):
-    """precision = 'bf16' (tcgen05 tensor cores, the throughput mode) or 'fp32' (CUDA-core FFMA,
-    max-abs <= 1e-4 against PyTorchCPURenderer)."""
+    """precision = 'bf16' (tcgen05 tensor cores, the throughput mode), 'bf16x3' (tensor cores with split
+    operands: max-abs ~1e-5 against PyTorchCPURenderer at a third of the bf16 rate) or 'fp32' (CUDA-core
+    FFMA, max-abs ~2e-6)."""
 
     def __init__(self, precision: str = "bf16", device_index: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA not available on this system")
         L.load_library()                       # raises if the CUDA library was not built
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        modes = {"bf16": L.BF16, "bf16x3": L.BF16X3, "fp32": L.FP32}
+        if precision not in modes:
+            raise ValueError("precision must be 'bf16', 'bf16x3' or 'fp32'")
         self.precision = precision
-        self.mode = L.BF16 if precision == "bf16" else L.FP32
+        self.mode = modes[precision]
         self.device_index = device_index
         super().__init__(f"B200 {precision.upper()}", "cuda")
         self._torch_device = torch.device("cuda", device_index)

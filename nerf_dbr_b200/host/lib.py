@@ -12,7 +12,7 @@ _PKG = os.path.dirname(_HERE)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libnerf_b200.so")
 
-FP32, BF16 = 0, 1
+FP32, BF16, BF16X3 = 0, 1, 2
 
 _lib = None
 

@@ -63,5 +63,7 @@ if which in ("all", "bf16"):
             r = rgb.cpu().reshape(-1, 3); rr = ref[0].reshape(-1, 3)
             print("   first rays got", r[:3].tolist(), "ref", rr[:3].tolist())
     for (W, H, S, it) in [(400, 300, 64, 5), (800, 600, 128, 5)]:
+        ms3 = timed(lambda: ops.render_image(net, pose, W, H, S, mode=2), 2)
+        print(f"bf16x3 {W}x{H}x{S}: {ms3:.3f} ms  {W*H/ms3/1e3:.3f} Mrays/s")
         ms = timed(lambda: ops.render_image(net, pose, W, H, S, mode=1), it)
         print(f"bf16 {W}x{H}x{S}: {ms:.3f} ms  {W*H/ms/1e3:.3f} Mrays/s  {W*H*S*1.055744e6/ms/1e9:.1f} TFLOP/s")
