@@ -141,6 +141,22 @@ NERF_B200_API int nerf_b200_render_rays(const void *packed, const float *rays_o,
                           int n_rays, int n_samples, float near, float far, const float *t_rand,
                           int mode, float *rgb_out, float *depth_out, float *acc_out, void *stream);
 
+/* render_rays_ex: render_rays with explicit per-ray depths in (z_vals [n_rays,n_samples], ascending; overrides
+ * near/far/t_rand) and the per-sample compositing weights out (weights_out [n_rays,n_samples]) -- the two
+ * hooks a hierarchical (coarse -> importance -> fine) render needs: the `weights` output of
+ * VolumeRenderer.volume_render (src/utils/rendering.py:131) feeds importance_sample (:54-100). Either may be NULL. */
+NERF_B200_API int nerf_b200_render_rays_ex(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
+                             int n_samples, float near, float far, const float *t_rand, const float *z_vals,
+                             int mode, float *rgb_out, float *depth_out, float *acc_out, float *weights_out,
+                             void *stream);
+
+/* merge_samples: sorted union of z_sorted [n_rays,n_sorted] (ascending) and z_new [n_rays,n_new] (any order) ->
+ * z_out [n_rays, n_sorted+n_new], equal to torch.sort(torch.cat([z, z_new], -1)).values bit for bit.  The
+ * reference stops at importance_sample (its result is never consumed); the sorted union is the original-NeRF
+ * recipe, needed because volume_render assumes ascending depths. */
+NERF_B200_API int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_rays, int n_sorted, int n_new,
+                            float *z_out, void *stream);
+
 /* ---- training ----------------------------------------------------------------------------
  * train_fwd_bwd: forward + backward of ONE network's term of the photometric loss in
  * NeRFTrainer.train_step (src/training/trainer.py:117-126):

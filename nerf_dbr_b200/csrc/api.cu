@@ -4,9 +4,9 @@
 namespace nerfb200 {
 int simt_query(const void *, const float *, const float *, long long, float *, float *, cudaStream_t);
 int simt_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, cudaStream_t);
-int simt_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, float *, float *, float *, cudaStream_t);
+int simt_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, const float *, float *, float *, float *, float *, cudaStream_t);
 int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, bool, float *, float *, unsigned int *, cudaStream_t);
-int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, bool, float *, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, const float *, bool, float *, float *, float *, float *, unsigned int *, cudaStream_t);
 }
 using namespace nerfb200;
 
@@ -45,20 +45,29 @@ int nerf_b200_render_image(const void *packed, const float *c2w_host, int width,
     return NERF_B200_EINVAL;
 }
 
-int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
-                          int n_samples, float near, float far, const float *t_rand, int mode,
-                          float *rgb_out, float *depth_out, float *acc_out, void *stream)
+int nerf_b200_render_rays_ex(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
+                             int n_samples, float near, float far, const float *t_rand, const float *z_vals, int mode,
+                             float *rgb_out, float *depth_out, float *acc_out, float *weights_out, void *stream)
 {
     if (!packed || !rays_o || !rays_d || !rgb_out || !depth_out || n_rays <= 0 || n_samples <= 0)
         return NERF_B200_EINVAL;
     if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
     if (mode == NERF_B200_FP32)
-        return simt_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, rgb_out,
-                                depth_out, acc_out, (cudaStream_t)stream);
+        return simt_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, z_vals, rgb_out,
+                                depth_out, acc_out, weights_out, (cudaStream_t)stream);
     if (mode == NERF_B200_BF16 || mode == NERF_B200_BF16X3)
-        return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, mode == NERF_B200_BF16X3,
-                              rgb_out, depth_out, acc_out, g_watchdog, (cudaStream_t)stream);
+        return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, z_vals,
+                              mode == NERF_B200_BF16X3, rgb_out, depth_out, acc_out, weights_out, g_watchdog,
+                              (cudaStream_t)stream);
     return NERF_B200_EINVAL;
+}
+
+int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
+                          int n_samples, float near, float far, const float *t_rand, int mode,
+                          float *rgb_out, float *depth_out, float *acc_out, void *stream)
+{
+    return nerf_b200_render_rays_ex(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, nullptr, mode,
+                                    rgb_out, depth_out, acc_out, nullptr, stream);
 }
 
 }  // extern "C"

@@ -247,6 +247,40 @@ __global__ void composite_kernel(const float *__restrict__ sigma, const float *_
     }
 }
 
+// ------------------------------------------------------------------------------ merge
+// Sorted union of the coarse depths (ascending) and the importance samples (any order): the depths a
+// hierarchical fine pass renders (original-NeRF recipe; the reference leaves it undefined).  One warp per
+// ray; every element's output position is its rank, so the result equals torch.sort(cat(z, z_new)).values
+// bit for bit.
+__global__ void merge_samples_kernel(const float *__restrict__ z_a, const float *__restrict__ z_b, int n_rays, int na,
+                                     int nb, float *__restrict__ z_out)
+{
+    extern __shared__ float sm_merge[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *a = sm_merge + (size_t)warp * (na + nb), *b = a + na;
+    for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
+        for (int i = lane; i < na; i += 32) a[i] = __ldg(z_a + (size_t)ray * na + i);
+        for (int i = lane; i < nb; i += 32) b[i] = __ldg(z_b + (size_t)ray * nb + i);
+        __syncwarp();
+        float *out = z_out + (size_t)ray * (na + nb);
+        for (int i = lane; i < na; i += 32) {              // a is sorted: rank = i + #{b < a_i}
+            float v = a[i];
+            int r = i;
+            for (int j = 0; j < nb; ++j) r += b[j] < v;
+            out[r] = v;
+        }
+        for (int i = lane; i < nb; i += 32) {              // rank = #{a <= b_i} + #{b < b_i} + #{j < i : b_j == b_i}
+            float v = b[i];
+            int lo = 0, hi = na;
+            while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
+            int r = lo;
+            for (int j = 0; j < nb; ++j) r += (b[j] < v) || (b[j] == v && j < i);
+            out[r] = v;
+        }
+        __syncwarp();
+    }
+}
+
 static inline int grid_for(size_t work_items, int block, int per_sm = 8)
 {
     int dev = 0, sms = 148;
@@ -315,6 +349,18 @@ int nerf_b200_importance_sample(const float *rays_o, const float *rays_d, const 
     size_t smem = (size_t)(block / 32) * (2 * n_samples + 2) * sizeof(float);
     importance_kernel<<<grid_for((size_t)n_rays * 32, block), block, smem, (cudaStream_t)stream>>>(
         rays_o, rays_d, z_vals, weights, u, n_rays, n_samples, n_new, (long long *)indices, z_new, points);
+    return launch_status();
+}
+
+int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_rays, int n_sorted, int n_new, float *z_out,
+                            void *stream)
+{
+    if (!z_sorted || !z_new || !z_out || n_rays <= 0 || n_sorted <= 0 || n_new <= 0) return NERF_B200_EINVAL;
+    if (n_sorted + n_new > 4096) return NERF_B200_EUNSUPPORTED;
+    const int block = 128;
+    size_t smem = (size_t)(block / 32) * (n_sorted + n_new) * sizeof(float);
+    merge_samples_kernel<<<grid_for((size_t)n_rays * 32, block), block, smem, (cudaStream_t)stream>>>(
+        z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
     return launch_status();
 }
 

@@ -28,6 +28,8 @@ struct SimtArgs {
     int width, row0;
     float half_w, half_h, focal;
     const float *rays_o, *rays_d, *t_rand;
+    const float *z_vals;                  // optional explicit depths [n_rays, n_samples]
+    float *weights;                       // optional compositing weights out [n_rays, n_samples]
     int n_rays, n_samples, rays_per_item;
     float near, far;
     float *rgb_map, *depth, *acc;
@@ -36,7 +38,8 @@ struct SimtArgs {
 // alpha compositing of one ray by one warp from shared (sigma,r,g,b); depths recomputed.
 // reference pytorch_renderers.py:105-125
 __device__ void simt_composite_ray(const float4 *__restrict__ smp, int n_samples, float near, float far,
-                                   const float *__restrict__ t_rand_ray, float dnorm, int lane,
+                                   const float *__restrict__ t_rand_ray, const float *__restrict__ z_ray,
+                                   float *__restrict__ w_ray, float dnorm, int lane,
                                    float &o_r, float &o_g, float &o_b, float &o_d, float &o_a)
 {
     const float step = linspace_step(n_samples);
@@ -47,11 +50,13 @@ __device__ void simt_composite_ray(const float4 *__restrict__ smp, int n_samples
         bool on = s < n_samples;
         float z = 0.f, zn = 0.f;
         if (on) {
-            z = t_rand_ray ? depth_jittered(s, n_samples, step, near, far, __ldg(t_rand_ray + s))
-                           : depth_uniform(s, n_samples, step, near, far);
+            z = z_ray ? __ldg(z_ray + s)
+                : t_rand_ray ? depth_jittered(s, n_samples, step, near, far, __ldg(t_rand_ray + s))
+                             : depth_uniform(s, n_samples, step, near, far);
             if (s + 1 < n_samples)
-                zn = t_rand_ray ? depth_jittered(s + 1, n_samples, step, near, far, __ldg(t_rand_ray + s + 1))
-                                : depth_uniform(s + 1, n_samples, step, near, far);
+                zn = z_ray ? __ldg(z_ray + s + 1)
+                     : t_rand_ray ? depth_jittered(s + 1, n_samples, step, near, far, __ldg(t_rand_ray + s + 1))
+                                  : depth_uniform(s + 1, n_samples, step, near, far);
         }
         float4 v = on ? smp[s] : make_float4(0.f, 0.f, 0.f, 0.f);
         float dist = __fmul_rn((s + 1 < n_samples) ? __fsub_rn(zn, z) : 1e10f, dnorm);
@@ -66,6 +71,7 @@ __device__ void simt_composite_ray(const float4 *__restrict__ smp, int n_samples
         float trans = (float)(carry * (lane == 0 ? 1.0 : excl));
         carry *= __shfl_sync(0xffffffffu, keep, 31);
         float w = __fmul_rn(alpha, trans);
+        if (w_ray && on) w_ray[s] = w;
         cr = fmaf(w, v.y, cr); cg = fmaf(w, v.z, cg); cb = fmaf(w, v.w, cb);
         cd = fmaf(w, z, cd); ca += w;
     }
@@ -138,8 +144,9 @@ __global__ void __launch_bounds__(kSimtThreads, 1) simt_mlp_kernel(SimtArgs a)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) { d[c] = __ldg(a.rays_d + 3 * (size_t)ray + c); o[c] = __ldg(a.rays_o + 3 * (size_t)ray + c); }
                     }
-                    float z = a.t_rand ? depth_jittered(s, S, step, a.near, a.far, __ldg(a.t_rand + (size_t)ray * S + s))
-                                       : depth_uniform(s, S, step, a.near, a.far);
+                    float z = a.z_vals ? __ldg(a.z_vals + (size_t)ray * S + s)
+                              : a.t_rand ? depth_jittered(s, S, step, a.near, a.far, __ldg(a.t_rand + (size_t)ray * S + s))
+                                         : depth_uniform(s, S, step, a.near, a.far);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) p[c] = point_on_ray(o[c], d[c], z);
                 }
@@ -170,7 +177,9 @@ __global__ void __launch_bounds__(kSimtThreads, 1) simt_mlp_kernel(SimtArgs a)
             float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
             float cr, cg, cb, cd, ca;
             simt_composite_ray(sm.out + (size_t)q * S, S, a.near, a.far,
-                               a.t_rand ? a.t_rand + (size_t)ray * S : nullptr, dn, lane, cr, cg, cb, cd, ca);
+                               a.t_rand ? a.t_rand + (size_t)ray * S : nullptr,
+                               a.z_vals ? a.z_vals + (size_t)ray * S : nullptr,
+                               a.weights ? a.weights + (size_t)ray * S : nullptr, dn, lane, cr, cg, cb, cd, ca);
             if (lane == 0) {
                 a.rgb_map[3 * (size_t)ray + 0] = cr; a.rgb_map[3 * (size_t)ray + 1] = cg; a.rgb_map[3 * (size_t)ray + 2] = cb;
                 a.depth[ray] = cd;
@@ -231,13 +240,13 @@ int simt_render_pose(const void *packed, const float *c2w, int width, int height
 }
 
 int simt_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays,
-                     int n_samples, float near, float far, const float *t_rand, float *rgb_out,
-                     float *depth_out, float *acc_out, cudaStream_t stream)
+                     int n_samples, float near, float far, const float *t_rand, const float *z_vals, float *rgb_out,
+                     float *depth_out, float *acc_out, float *weights_out, cudaStream_t stream)
 {
     if (n_samples > kItemMax) return NERF_B200_EUNSUPPORTED;
     SimtArgs a = {};
     a.wf = reinterpret_cast<const float *>(packed);
-    a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
+    a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand; a.z_vals = z_vals; a.weights = weights_out;
     a.n_rays = n_rays; a.n_samples = n_samples; a.rays_per_item = rays_per_item_for(n_samples);
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out;

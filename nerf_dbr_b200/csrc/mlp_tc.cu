@@ -108,6 +108,8 @@ struct Args {
     int width, row0;
     float half_w, half_h, focal;
     const float *rays_o, *rays_d, *t_rand;
+    const float *z_vals;       // optional explicit depths [n_rays, n_samples] (ascending per ray)
+    float *weights;            // optional per-sample compositing weights out [n_rays, n_samples]
     int n_rays, n_samples;
     int s_pad_log2;            // S_pad = 1 << s_pad_log2 when tiles_per_ray == 1
     int tiles_per_ray;         // > 1 when S_pad > 128
@@ -172,6 +174,7 @@ __device__ __forceinline__ void ray_of(const Args &a, int ray, float (&o)[3], fl
 
 __device__ __forceinline__ float depth_of(const Args &a, int ray, int s, float step)
 {
+    if (a.z_vals) return __ldg(a.z_vals + (size_t)ray * a.n_samples + s);
     return a.t_rand ? depth_jittered(s, a.n_samples, step, a.near, a.far, __ldg(a.t_rand + (size_t)ray * a.n_samples + s))
                     : depth_uniform(s, a.n_samples, step, a.near, a.far);
 }
@@ -320,6 +323,7 @@ __device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int
         trans *= pre;
     }
     float w = __fmul_rn(alpha, trans);
+    if (a.weights && ri.valid) a.weights[(size_t)ri.ray * a.n_samples + ri.s] = w;
     float sums[5] = {w * col[0], w * col[1], w * col[2], w * z, w};
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -754,10 +758,11 @@ int tc_render_pose(const void *packed, const float *c2w, int width, int height, 
 }
 
 int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples,
-                   float near, float far, const float *t_rand, bool split, float *rgb_out, float *depth_out,
-                   float *acc_out, unsigned int *dbg, cudaStream_t stream)
+                   float near, float far, const float *t_rand, const float *z_vals, bool split, float *rgb_out,
+                   float *depth_out, float *acc_out, float *weights_out, unsigned int *dbg, cudaStream_t stream)
 {
     tc::Args a = {};
+    a.z_vals = z_vals; a.weights = weights_out;
     a.packed = reinterpret_cast<const unsigned char *>(packed);
     a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
     a.n_rays = n_rays; a.n_samples = n_samples;

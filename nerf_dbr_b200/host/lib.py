@@ -53,6 +53,9 @@ PROTOTYPES = {
                                        c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_render_rays": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nerf_b200_render_rays_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
+                                         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nerf_b200_merge_samples": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "nerf_b200_train_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nerf_b200_train_fwd_bwd": (c_int, [c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Params), c_void_p,
                                         c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_int,

@@ -167,7 +167,10 @@ def render_image(packed: torch.Tensor, pose: torch.Tensor, width: int, height: i
 
 
 def render_rays(packed: torch.Tensor, rays_o, rays_d, n_samples: int, mode: int = L.BF16,
-                near: float = 2.0, far: float = 6.0, t_rand=None, want_acc: bool = False):
+                near: float = 2.0, far: float = 6.0, t_rand=None, want_acc: bool = False, z_vals=None,
+                want_weights: bool = False):
+    """Fused render of a ray batch.  ``z_vals`` [R,S] (ascending) overrides the uniform/stratified depths;
+    ``want_weights`` also returns the per-sample compositing weights [R,S]."""
     lib = L.load_library()
     ro, rd = _dev(rays_o, "render_rays"), _dev(rays_d, "render_rays")
     n = ro.shape[0]
@@ -175,11 +178,42 @@ def render_rays(packed: torch.Tensor, rays_o, rays_d, n_samples: int, mode: int 
     depth = torch.empty(n, device=ro.device)
     acc = torch.empty(n, device=ro.device) if want_acc else None
     tr = None if t_rand is None else _dev(t_rand, "render_rays")
+    zv = None if z_vals is None else _dev(z_vals, "render_rays")
+    if zv is not None and tuple(zv.shape) != (n, n_samples):
+        raise ValueError("z_vals must be [n_rays, n_samples]")
+    wts = torch.empty(n, n_samples, device=ro.device) if want_weights else None
     with torch.cuda.device(ro.device):
-        L.check("nerf_b200_render_rays", lib.nerf_b200_render_rays(
-            _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), mode,
-            _ptr(rgb), _ptr(depth), _ptr(acc), _stream()))
-    return (rgb, depth, acc) if want_acc else (rgb, depth)
+        L.check("nerf_b200_render_rays_ex", lib.nerf_b200_render_rays_ex(
+            _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), _ptr(zv), mode,
+            _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(wts), _stream()))
+    out = (rgb, depth) + ((acc,) if want_acc else ()) + ((wts,) if want_weights else ())
+    return out
+
+
+def merge_samples(z_sorted, z_new) -> torch.Tensor:
+    lib = L.load_library()
+    a, b = _dev(z_sorted, "merge_samples"), _dev(z_new, "merge_samples")
+    out = torch.empty(a.shape[0], a.shape[1] + b.shape[1], device=a.device)
+    with torch.cuda.device(a.device):
+        L.check("nerf_b200_merge_samples", lib.nerf_b200_merge_samples(
+            _ptr(a), _ptr(b), a.shape[0], a.shape[1], b.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def render_hierarchical(coarse_packed, fine_packed, rays_o, rays_d, n_coarse: int, n_importance: int,
+                        mode: int = L.BF16, near: float = 2.0, far: float = 6.0, u=None, t_rand=None):
+    """Coarse pass -> inverse-CDF importance samples -> fine pass on the sorted union (BASELINE.json configs[4]:
+    128 coarse + 128 importance).  ``u`` [R,n_importance] uniforms (drawn here when None).  Returns
+    (rgb_fine, depth_fine, rgb_coarse, z_union)."""
+    ro, rd = _dev(rays_o, "render_hierarchical"), _dev(rays_d, "render_hierarchical")
+    rgb_c, _, wts = render_rays(coarse_packed, ro, rd, n_coarse, mode, near, far, t_rand, want_weights=True)
+    _, z_c = sample_points(ro, rd, n_coarse, near, far, t_rand)
+    if u is None:
+        u = torch.rand(ro.shape[0], n_importance, device=ro.device)
+    _, z_new, _ = importance_sample(ro, rd, z_c, wts, u)
+    z_all = merge_samples(z_c, z_new)
+    rgb_f, depth_f = render_rays(fine_packed, ro, rd, n_coarse + n_importance, mode, near, far, z_vals=z_all)
+    return rgb_f, depth_f, rgb_c, z_all
 
 
 _workspaces = {}
