@@ -156,6 +156,77 @@ def run_reference(args):
     emit(line)
 
 
+def run_train(args):
+    """BASELINE.json configs[3]: 4096-ray batch, coarse 64 jittered + fine 128 uniform samples, forward + backward of
+    mse(coarse)+mse(fine), data-parallel (ray batch sharded, one NCCL gradient all-reduce) + Adam step.  Not the
+    headline metric -- printed with its own metric name."""
+    import torch
+    import torch.distributed as dist
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host.parallel import ray_shard
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    from oracle import nerf_oracle as O
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_rays, n_c, n_f = 4096, 64, 128
+    ck = O.seeded_checkpoint(5, 30.0)
+    coarse, fine = nb.NeRFModel().to(dev), nb.NeRFModel().to(dev)
+    coarse.load_state_dict(ck["coarse_model"]); fine.load_state_dict(ck["fine_model"])
+    step = B200TrainStep(coarse, fine, n_c, n_f)
+    opt = torch.optim.Adam(step.parameters(), lr=5e-4)
+    pose = torch.eye(4); pose[2, 3] = 4.0
+    ro, rd = O.camera_rays(pose, 200, 150)
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(150, 200, 3, generator=g)
+    first, count = ray_shard(rank, world, n_rays)
+    batches = []
+    for i in range(args.steps + args.warmup):
+        sel = torch.randperm(200 * 150, generator=g)[:n_rays][first:first + count]
+        batches.append((ro.reshape(-1, 3)[sel].to(dev), rd.reshape(-1, 3)[sel].to(dev), image.reshape(-1, 3)[sel].to(dev),
+                        torch.rand(count, n_c, generator=g).to(dev)))
+
+    def one(i):
+        b = batches[i]
+        loss, _, _ = step(b[0], b[1], b[2], t_rand=b[3], n_rays_global=n_rays)
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        loss = one(args.warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        flop = 3_095_808 * n_rays * (n_c + n_f)
+        emit({"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+Adam", "value": n_rays / (ms * 1e-3),
+              "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
+                         "loss_last": float(loss)},
+              "gpu_launches": int(ops.launch_count() - n0),
+              "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peaks()["bf16_tflops"],
+                           "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peaks()["bf16_tflops"], "traffic": None,
+                           "note": "FP32 CUDA-core kernels; tensor-core training kernels are the next step"}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,10 +235,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = the headline metric (default); train = BASELINE.json configs[3], extra evidence")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

@@ -81,6 +81,17 @@ class B200Renderer(_Base):
         return ops.render_image(self._net(True), camera_pose, width, height, samples_per_ray, self.mode,
                                 800.0, self.near, self.far)
 
+    def render_image_hierarchical(self, camera_pose, resolution: Tuple[int, int], n_coarse: int = 128,
+                                  n_importance: int = 128, u=None):
+        """Two-pass render (BASELINE.json configs[4]): coarse network on ``n_coarse`` uniform samples, inverse-CDF
+        importance samples from its weights (VolumeRenderer.importance_sample, rendering.py:54-100), fine network
+        on the sorted union.  Returns (rgb [H,W,3], depth [H,W])."""
+        width, height = resolution
+        ro, rd = self.generate_rays(camera_pose, width, height)
+        rgb, depth, _, _ = ops.render_hierarchical(self._net(False), self._net(True), ro.reshape(-1, 3), rd.reshape(-1, 3),
+                                                   n_coarse, n_importance, self.mode, self.near, self.far, u)
+        return rgb.reshape(height, width, 3), depth.reshape(height, width)
+
     def render_rows(self, camera_pose, resolution: Tuple[int, int], samples_per_ray: int, row0: int, n_rows: int,
                     out_rgb=None, out_depth=None):
         """The multi-GPU shard: rows [row0, row0+n_rows) of the image."""

@@ -30,8 +30,9 @@ def test_merge_is_bit_exact_sorted_union():
         assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("mode,tol", [(0, 2e-6), (2, 2e-5), (1, 3e-2)])
-def test_weights_output_and_explicit_depths(mode, tol, checkpoints, poses):
+# (mode, weights tolerance, rgb/depth/acc tolerance): fp32 and bf16x3 are held to the 1e-4 gate
+@pytest.mark.parametrize("mode,tol,tol_img", [(0, 5e-6, 1e-4), (2, 1e-4, 1e-4), (1, 3e-2, 1e-1)])
+def test_weights_output_and_explicit_depths(mode, tol, tol_img, checkpoints, poses):
     from nerf_dbr_b200.host import ops
     w = checkpoints["lego"]["fine_model"]
     net = packed_net(w)
@@ -41,7 +42,7 @@ def test_weights_output_and_explicit_depths(mode, tol, checkpoints, poses):
             _, z = O.sample_along_rays(ro, rd, S)
             ref = O.render_rays_at(w, ro, rd, z.contiguous())
             rgb, dep, acc, wts = ops.render_rays(net, ro.cuda(), rd.cuda(), S, mode=mode, want_acc=True, want_weights=True)
-            assert (wts.cpu() - ref[3]).abs().max() <= tol and (acc.cpu() - ref[2]).abs().max() <= 50 * tol
+            assert (wts.cpu() - ref[3]).abs().max() <= tol and (acc.cpu() - ref[2]).abs().max() <= tol_img
         # explicit, non-uniform, ascending depths (256 = two tiles per ray in the tensor-core kernel)
         g = torch.Generator().manual_seed(4)
         z = torch.sort(torch.rand(ro.shape[0], 256, generator=g) * 4 + 2, dim=-1).values
@@ -50,7 +51,7 @@ def test_weights_output_and_explicit_depths(mode, tol, checkpoints, poses):
         torch.cuda.synchronize()
         assert int(wd.word.item()) == 0
         assert (wts.cpu() - ref[3]).abs().max() <= tol
-        assert (rgb.cpu() - ref[0]).abs().max() <= 60 * tol and (dep.cpu() - ref[1]).abs().max() <= 200 * tol
+        assert (rgb.cpu() - ref[0]).abs().max() <= tol_img and (dep.cpu() - ref[1]).abs().max() <= tol_img
 
 
 def test_hierarchical_render_end_to_end_fp32(checkpoints, poses):
@@ -66,8 +67,10 @@ def test_hierarchical_render_end_to_end_fp32(checkpoints, poses):
     assert z_all.shape == (ro.shape[0], 256)
     assert bool((z_all[:, 1:] >= z_all[:, :-1]).all())
     assert (rgb_c.cpu() - ref_c).abs().max() <= 1e-4
-    same = (z_all.cpu() == z_ref).float().mean().item()
-    assert same >= 0.995, same
+    # the inverse CDF is continuous in the weights: 1e-6 differences in the coarse weights move a new depth by
+    # ulps (or, inside a near-empty bin, by a visible fraction of that bin) -- never to another region
+    dz = (z_all.cpu() - z_ref).abs()
+    assert (dz == 0).float().mean().item() >= 0.98 and (dz <= 1e-4).float().mean().item() >= 0.995, dz.max()
     assert (rgb_f.cpu() - ref_f).abs().max() <= 2e-3 and (dep_f.cpu() - ref_d).abs().max() <= 2e-2
 
 
