@@ -177,7 +177,8 @@ def run_train(args):
     ck = O.seeded_checkpoint(5, 30.0)
     coarse, fine = nb.NeRFModel().to(dev), nb.NeRFModel().to(dev)
     coarse.load_state_dict(ck["coarse_model"]); fine.load_state_dict(ck["fine_model"])
-    step = B200TrainStep(coarse, fine, n_c, n_f)
+    from nerf_dbr_b200.host import lib as L
+    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32)
     opt = torch.optim.Adam(step.parameters(), lr=5e-4)
     pose = torch.eye(4); pose[2, 3] = 4.0
     ro, rd = O.camera_rays(pose, 200, 150)
@@ -216,7 +217,8 @@ def run_train(args):
         flop = 3_095_808 * n_rays * (n_c + n_f)
         emit({"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+Adam", "value": n_rays / (ms * 1e-3),
               "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "bf16 wgrad / f32 forward+dgrad" if args.precision == "bf16" else "f32", "data": "synthetic",
               "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
                          "loss_last": float(loss)},
               "gpu_launches": int(ops.launch_count() - n0),

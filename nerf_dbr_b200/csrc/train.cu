@@ -14,15 +14,21 @@
 //                         64x64 output tiles, split over samples, fp32 atomics into the caller's grads
 // Gradients are ACCUMULATED (+=), pre-scaled by 2 / (3 R_global) so data-parallel ranks all-reduce-sum.
 //
-// The tensor-core (bf16) training kernels are the next step; this mode is the gradient
-// parity reference on the device (max relative error ~1e-5 against the reference's autograd).
+// FP32 mode is the gradient parity reference on the device (relative error <= 5e-4 against the reference's
+// autograd).  BF16 mode moves the weight-gradient GEMMs (40 % of the FP32 step) to the tensor cores
+// (train_tc.cu); forward and dgrad chain on the tensor cores are the next step.
 #include <algorithm>
 #include "common.cuh"
 #include "simt_tile.cuh"
 
 namespace nerfb200 {
 
-constexpr int kChunkSamples = 32768;         // samples per chunk (multiple of 64)
+constexpr int kChunkSamples = 262144;        // samples per chunk (multiple of 64): 4.7 GB of workspace at most
+constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per SM over the chunk's samples
+
+size_t wgrad_tc_scratch_bytes(int splits);
+int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
+             float *dbias, float *scratch, int splits, cudaStream_t stream);
 
 // workspace rows ([row][CH] floats)
 constexpr int R_PE = 0;                      // 64
@@ -378,7 +384,7 @@ size_t nerf_b200_train_workspace_bytes(int n_rays, int n_samples)
     if (n_rays <= 0 || n_samples <= 0) return 0;
     long long per = (long long)std::min(n_rays, chunk_rays(n_samples)) * n_samples;
     long long ch = (per + 63) / 64 * 64;
-    return (size_t)ch * R_TOTAL * sizeof(float);
+    return (size_t)ch * R_TOTAL * sizeof(float) + wgrad_tc_scratch_bytes(kWgradSplits);
 }
 
 int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, const nerf_b200_params *grads,
@@ -390,7 +396,8 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
     if (!packed || !grads || !rays_o || !rays_d || !target || !workspace || !loss_sum || n_rays <= 0 ||
         n_samples <= 0 || n_rays_global <= 0)
         return NERF_B200_EINVAL;
-    if (mode != NERF_B200_FP32) return NERF_B200_EUNSUPPORTED;       // tensor-core training kernels: next
+    if (mode != NERF_B200_FP32 && mode != NERF_B200_BF16) return NERF_B200_EUNSUPPORTED;
+    const bool tc = mode == NERF_B200_BF16;      // BF16: weight gradients on the tensor cores (bf16 operands, fp32 accumulate)
     if (n_samples > kChunkSamples) return NERF_B200_EUNSUPPORTED;
     if (((uintptr_t)packed & 1023) || ((uintptr_t)workspace & 15)) return NERF_B200_EALIGN;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -424,8 +431,12 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         const size_t ch = a.ch;
         auto row = [&](int r) { return ws + (size_t)r * ch; };
         const int split = std::max(1, std::min(64, (int)(ch / 2048)));
+        float *scratch = ws + (size_t)R_TOTAL * ch;
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
+            if (tc && rows_a >= 128)
+                return wgrad_tc(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off, const_cast<float *>(db),
+                                scratch, kWgradSplits, stream);
             dim3 grid((rows_a + 63) / 64, (rows_b + 63) / 64, split);
             wgrad_kernel<<<grid, 256, 0, stream>>>(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
                                                    const_cast<float *>(db));

@@ -132,3 +132,32 @@ def test_adam_step_follows_reference_trainer(checkpoints):
             num += float((d_gpu - d_cpu).norm() ** 2)
             den += float(d_cpu.norm() ** 2)
     assert (num / den) ** 0.5 <= 0.05, (num / den) ** 0.5
+
+
+def test_train_step_bf16_mode_tensor_core_wgrad():
+    """BF16 mode (weight gradients on the tensor cores, bf16 operands): per-tensor relative error <= 1e-2
+    against the reference's fp32 autograd on the golden train step; loss unchanged (forward is fp32)."""
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    g = load_npz("golden_train.npz")
+    ck = O.seeded_checkpoint(int(g["seed"]), float(g["density_gain"]))
+    coarse, fine = models_from(ck)
+    H, W = int(g["H"]), int(g["W"])
+    image = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(0))
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+    ro, rd = O.camera_rays(pose, W, H)
+    sel = torch.from_numpy(g["select"])
+    ro, rd, tgt = ro.reshape(-1, 3)[sel].cuda(), rd.reshape(-1, 3)[sel].cuda(), image.reshape(-1, 3)[sel].cuda()
+    step = B200TrainStep(coarse, fine, 64, 128, mode=1)
+    loss, _, _ = step(ro, rd, tgt, t_rand=torch.from_numpy(g["t_rand"]).cuda())
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    rows = []
+    for tag, m in (("coarse", coarse), ("fine", fine)):
+        for name, p in m.named_parameters():
+            got = p.grad.reshape(-1).cpu()
+            ref = torch.from_numpy(g[f"{tag}|{name}|strided"])
+            err = float((got[::37] - ref).double().norm()) / max(float(ref.double().norm()), 1e-30)
+            rows.append((err, tag, name))
+    rows.sort(reverse=True)
+    print("bf16-mode worst relative gradient errors:", [(f"{e:.1e}", t, k) for e, t, k in rows[:5]])
+    assert rows[0][0] <= 1e-2, rows[0]
