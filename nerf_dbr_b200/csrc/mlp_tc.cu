@@ -47,6 +47,7 @@
 #include <utility>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "train_layout.h"
 
 namespace nerfb200 {
 namespace tc {
@@ -116,6 +117,8 @@ struct Args {
     int n_tiles, tiles_per_cta;
     float near, far;
     float *rgb_map, *depth, *acc;
+    float *ws;                 // TRAIN: training workspace [R_TOTAL][ws_ch] (train_layout.h); rays are chunk-local
+    int ws_ch;
     unsigned int *dbg;         // optional: [0] = first timeout code
     long long *trace;          // optional timeline (tools/tc_trace.py): CTA 0, first kTraceTiles tiles
 };
@@ -156,6 +159,9 @@ __device__ __forceinline__ RowInfo row_info(const Args &a, int tile, int row)
     r.valid = r.ray < a.n_rays && r.s < a.n_samples;
     return r;
 }
+
+// TRAIN: column of the workspace this tile row maps to (-1: padding row)
+__device__ __forceinline__ int ws_col(const Args &a, const RowInfo &ri) { return ri.valid ? ri.ray * a.n_samples + ri.s : -1; }
 
 template <int SRC>
 __device__ __forceinline__ void ray_of(const Args &a, int ray, float (&o)[3], float (&d)[3])
@@ -198,7 +204,7 @@ __device__ __forceinline__ void sincos_phase(uint32_t phase, float &s, float &c)
 // front: rays, depths, points, encoded-position tile (bf16, swizzled) and per-ray colour bias
 __device__ __forceinline__ float bf16_hi(float v) { return __uint_as_float(__float_as_uint(__bfloat162float(__float2bfloat16_rn(v)))); }
 
-template <int SRC, bool SPLIT>
+template <int SRC, bool SPLIT, bool TRAIN>
 __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, int rb_buf, int row, float step,
                              const float *__restrict__ wf)
 {
@@ -226,6 +232,14 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
                 feat[3 + 6 * k + c] = sn;
                 feat[3 + 6 * k + 3 + c] = cs;
             }
+    }
+    if (TRAIN) {                                           // the bf16 values the MMA sees, [feature][sample] for wgrad
+        const int col = ws_col(a, ri);
+        if (col >= 0) {
+            float *p = a.ws + (size_t)R_PE * a.ws_ch + col;
+#pragma unroll
+            for (int f = 0; f < 64; ++f) p[(size_t)f * a.ws_ch] = bf16_hi(feat[f]);
+        }
     }
     const uint32_t pe_row = smem_u32(sm + SM_PE + pe_buf * 16384 + row * 128);
 #pragma unroll
@@ -270,6 +284,15 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
 #pragma unroll
         for (int j = 0; j < kDirFeat; ++j) acc = fmaf(de[q * 32 + j], __ldg(wf + F_WC0D + j * 128 + row), acc);
         rayb[q * 128 + row] = acc;
+    }
+    if (TRAIN) {                                           // encoded direction of this row's ray (dW of colour layer 0)
+        const int col = ws_col(a, ri);
+        if (col >= 0) {
+            const int q = a.tiles_per_ray == 1 ? (row >> a.s_pad_log2) : 0;
+            float *p = a.ws + (size_t)R_DE * a.ws_ch + col;
+#pragma unroll
+            for (int f = 0; f < kDirFeat; ++f) p[(size_t)f * a.ws_ch] = de[q * 32 + f];
+        }
     }
     named_bar_sync(1, 128);          // de[] is rewritten by the next produce
 }
@@ -414,8 +437,10 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
     }
 }
 
+// ws_out (TRAIN): &workspace[first feature of this warp's 64][this row's sample] or nullptr; ws_ch = row pitch
 template <bool SPLIT>
-__device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane)
+__device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
+                                              float *ws_out = nullptr, int ws_ch = 0)
 {
     uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
@@ -426,6 +451,13 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
         bias_relu_pack(xa, pk, bias_addr);
         bias_relu_pack(xb, pk + 16, bias_addr + 128);
         tmem_st32(t_cols, pk);                   // K-block: 64 bf16 in columns [0, 32) of this warp's range
+        if (ws_out) {                            // exactly what the next layer multiplies: the bf16-rounded values
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                ws_out[(size_t)(2 * i) * ws_ch] = __uint_as_float(pk[i] << 16);
+                ws_out[(size_t)(2 * i + 1) * ws_ch] = __uint_as_float(pk[i] & 0xffff0000u);
+            }
+        }
     } else {
         uint32_t hi[16], lo[16];                 // hi halves in columns [0, 32), lo halves in [32, 64)
         bias_relu_pack_split(xa, hi, lo, bias_addr);
@@ -483,6 +515,48 @@ __device__ __forceinline__ void color_row(uint32_t t_row, uint32_t rayb_addr, ui
     sig_pre = __uint_as_float(sg);
     color_dot(xa, rayb_addr + 256, wc1_addr + 256, r0, r1, r2);
     color_dot(xb, rayb_addr + 384, wc1_addr + 384, r0, r1, r2);
+}
+
+// TRAIN back warps: this row of colour layer 0's accumulator -> relu(acc + per-ray bias) stored as colour layer
+// 0's activation, colour pre-activations -> sigmoid -> stored, density pre-activation stored.  No compositing:
+// the training step's ray kernel does forward compositing, loss and backward in one pass.
+__device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_addr, uint32_t wc1_addr, uint32_t bar_c0free,
+                                                int lane, const float *__restrict__ wf, float *ws, int ws_ch, int col)
+{
+    float r[3] = {0.f, 0.f, 0.f};
+    const uint32_t sg = tmem_ld1(t_row + 128);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t x[32];
+        tmem_ld32(t_row + 32 * g, x);
+        tmem_ld_wait();
+        if (g == 3) {                                       // the accumulator is in registers
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_c0free);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = ld_shared_f4(rayb_addr + (32 * g + 4 * i) * 4);
+            const float4 w0 = ld_shared_f4(wc1_addr + (32 * g + 4 * i) * 4);
+            const float4 w1 = ld_shared_f4(wc1_addr + 512 + (32 * g + 4 * i) * 4);
+            const float4 w2 = ld_shared_f4(wc1_addr + 1024 + (32 * g + 4 * i) * 4);
+            float v[4] = {fmaxf(__uint_as_float(x[4 * i + 0]) + b.x, 0.f), fmaxf(__uint_as_float(x[4 * i + 1]) + b.y, 0.f),
+                          fmaxf(__uint_as_float(x[4 * i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(x[4 * i + 3]) + b.w, 0.f)};
+            r[0] = fmaf(v[0], w0.x, r[0]); r[0] = fmaf(v[1], w0.y, r[0]); r[0] = fmaf(v[2], w0.z, r[0]); r[0] = fmaf(v[3], w0.w, r[0]);
+            r[1] = fmaf(v[0], w1.x, r[1]); r[1] = fmaf(v[1], w1.y, r[1]); r[1] = fmaf(v[2], w1.z, r[1]); r[1] = fmaf(v[3], w1.w, r[1]);
+            r[2] = fmaf(v[0], w2.x, r[2]); r[2] = fmaf(v[1], w2.y, r[2]); r[2] = fmaf(v[2], w2.z, r[2]); r[2] = fmaf(v[3], w2.w, r[2]);
+            if (col >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ws[(size_t)(R_C0H + 32 * g + 4 * i + j) * ws_ch + col] = v[j];
+            }
+        }
+    }
+    if (col >= 0) {
+        ws[(size_t)R_SIGPRE * ws_ch + col] = __uint_as_float(sg) + __ldg(wf + F_BSIG);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ws[(size_t)(R_RGB + c) * ws_ch + col] = 1.0f / (1.0f + expf(-(r[c] + __ldg(wf + F_BC1 + c))));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -562,7 +636,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx &x, std::integer_seque
 }
 
 // ------------------------------------------------------------------------------------------
-template <int SRC, bool SPLIT>
+template <int SRC, bool SPLIT, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 {
     using C = Cfg<SPLIT>;
@@ -656,8 +730,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     wait_bar(bar(B_ACCFULL + hh), layer & 1, a.dbg, 5);      // 8 phases per tile: parity = layer
                     tc_fence_after_sync();
                     if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
+                    float *ws_out = nullptr;
+                    if (TRAIN) {
+                        const int col = ws_col(a, row_info(a, tile_begin + t, row));
+                        if (col >= 0) ws_out = a.ws + (size_t)(R_H + layer * 256 + hh * 128 + 64 * w2) * a.ws_ch + col;
+                    }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                         bar(B_AREADY + 2 * hh + w2), lane);
+                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, a.ws_ch);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();
@@ -671,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         auto produce = [&](int t) {
             const int pb = SPLIT ? 0 : (t & 1), pe_use = SPLIT ? t : (t >> 1);
             if (pe_use >= 1) wait_bar(bar(B_PEEMPTY + pb), (pe_use - 1) & 1, a.dbg, 8);
-            produce_tile<SRC, SPLIT>(a, sm, tile_begin + t, pb, t & 1, row, step, wf);
+            produce_tile<SRC, SPLIT, TRAIN>(a, sm, tile_begin + t, pb, t & 1, row, step, wf);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_PEFULL + pb));
@@ -685,10 +764,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             tc_fence_after_sync();
             const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
             const uint32_t t_row = tmem_base + ((uint32_t)((warp - 12) * 32) << 16) + (uint32_t)(t & 1) * 256;
-            float ypre[3], sig_pre;
-            color_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
-                      bar(B_C0FREE), lane, ypre[0], ypre[1], ypre[2], sig_pre);
-            composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, 0, sig_pre, ypre);
+            if (TRAIN) {
+                train_heads_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
+                                bar(B_C0FREE), lane, wf, a.ws, a.ws_ch, ws_col(a, row_info(a, tile_begin + t, row)));
+            } else {
+                float ypre[3], sig_pre;
+                color_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
+                          bar(B_C0FREE), lane, ypre[0], ypre[1], ypre[2], sig_pre);
+                composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, 0, sig_pre, ypre);
+            }
         }
     }
 
@@ -726,14 +810,14 @@ static int plan(Args &a)
     return (a.n_tiles + per - 1) / per;               // grid
 }
 
-template <int SRC, bool SPLIT>
+template <int SRC, bool SPLIT, bool TRAIN = false>
 static int launch(Args &a, cudaStream_t stream)
 {
     int grid = plan(a);
     if (grid < 0) return grid;
-    cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC, SPLIT, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    fused_render_kernel<SRC, SPLIT><<<grid, kThreads, kSmemBytes, stream>>>(a);
+    fused_render_kernel<SRC, SPLIT, TRAIN><<<grid, kThreads, kSmemBytes, stream>>>(a);
     return launch_status();
 }
 
@@ -769,6 +853,20 @@ int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d,
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
     return split ? tc::launch<tc::SRC_RAYS, true>(a, stream) : tc::launch<tc::SRC_RAYS, false>(a, stream);
+}
+
+// Training forward on the tensor cores: rays [0, n_rays) of the given (chunk-local) arrays; activations, head
+// outputs and encodings go to the workspace (train_layout.h) for the ray kernel, the dgrad chain and wgrad.
+int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
+                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream)
+{
+    tc::Args a = {};
+    a.packed = reinterpret_cast<const unsigned char *>(packed);
+    a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
+    a.n_rays = n_rays; a.n_samples = n_samples;
+    a.near = near; a.far = far;
+    a.ws = ws; a.ws_ch = ws_ch; a.dbg = dbg;
+    return tc::launch<tc::SRC_RAYS, false, true>(a, stream);
 }
 
 }  // namespace nerfb200

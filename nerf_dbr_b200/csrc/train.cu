@@ -15,33 +15,24 @@
 // Gradients are ACCUMULATED (+=), pre-scaled by 2 / (3 R_global) so data-parallel ranks all-reduce-sum.
 //
 // FP32 mode is the gradient parity reference on the device (relative error <= 5e-4 against the reference's
-// autograd).  BF16 mode moves the weight-gradient GEMMs (40 % of the FP32 step) to the tensor cores
-// (train_tc.cu); forward and dgrad chain on the tensor cores are the next step.
+// autograd).  BF16 mode runs the forward (the fused tcgen05 kernel's TRAIN variant, which stores the
+// activations it multiplies) and the weight-gradient GEMMs (train_tc.cu) on the tensor cores; the dgrad
+// chain on the tensor cores is the next step.
 #include <algorithm>
 #include "common.cuh"
 #include "simt_tile.cuh"
+#include "train_layout.h"
 
 namespace nerfb200 {
 
 constexpr int kChunkSamples = 262144;        // samples per chunk (multiple of 64): 4.7 GB of workspace at most
 constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per SM over the chunk's samples
 
+int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
+                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
 int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream);
-
-// workspace rows ([row][CH] floats)
-constexpr int R_PE = 0;                      // 64
-constexpr int R_H = R_PE + 64;               // 8 x 256
-constexpr int R_C0H = R_H + 8 * 256;         // 128
-constexpr int R_DE = R_C0H + 128;            // 32
-constexpr int R_SIGPRE = R_DE + 32;          // 1   density head pre-activation
-constexpr int R_RGB = R_SIGPRE + 1;          // 3   post-sigmoid colour
-constexpr int R_DSIG = R_RGB + 3;            // 1   dL/d sigma_pre
-constexpr int R_DY = R_DSIG + 1;             // 3   dL/d colour pre-sigmoid
-constexpr int R_DPRE = R_DY + 3;             // 8 x 256   dL/d pre-activation of trunk layers
-constexpr int R_DPREC0 = R_DPRE + 8 * 256;   // 128
-constexpr int R_TOTAL = R_DPREC0 + 128;
 
 struct TrainArgs {
     const float *wf;                         // fp32 region of the packed weights
@@ -421,8 +412,21 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         a.loss_sum = loss_sum; a.rgb_out = rgb_out;
         const int tiles = a.ch / TM;
         int rc;
-        train_fwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
-        if ((rc = launch_status())) return rc;
+        if (tc) {
+            // forward on the tensor cores (TRAIN variant of the fused kernel); pad columns of the stored
+            // activations must be finite zeros: wgrad multiplies them by zero gradients
+            const int n_smp = a.n_rays * n_samples;
+            if (a.ch != n_smp)
+                cudaMemset2DAsync(a.ws + n_smp, (size_t)a.ch * sizeof(float), 0, (size_t)(a.ch - n_smp) * sizeof(float),
+                                  R_DE + 32, stream);
+            const float *tr = t_rand ? t_rand + (size_t)r0 * n_samples : nullptr;
+            if ((rc = tc_train_forward(packed, rays_o + 3 * (size_t)r0, rays_d + 3 * (size_t)r0, a.n_rays, n_samples, near, far,
+                                       tr, a.ws, a.ch, nullptr, stream)))
+                return rc;
+        } else {
+            train_fwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
+            if ((rc = launch_status())) return rc;
+        }
         train_ray_kernel<<<std::min((a.n_rays + 7) / 8, sms * 8), 256, 0, stream>>>(a);
         if ((rc = launch_status())) return rc;
         train_bwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);

@@ -1,0 +1,16 @@
+// Training workspace layout shared by train.cu (FP32 kernels), train_tc.cu and the TRAIN variant of the fused
+// tensor-core kernel (mlp_tc.cu): [row][ch] fp32, K-major for the weight-gradient GEMMs (sample contiguous).
+#pragma once
+namespace nerfb200 {
+constexpr int R_PE = 0;                      // 64   encoded position (row 63 = 0)
+constexpr int R_H = R_PE + 64;               // 8 x 256   post-ReLU trunk activations
+constexpr int R_C0H = R_H + 8 * 256;         // 128  post-ReLU colour layer 0
+constexpr int R_DE = R_C0H + 128;            // 32   encoded direction (27 used)
+constexpr int R_SIGPRE = R_DE + 32;          // 1    density head pre-activation
+constexpr int R_RGB = R_SIGPRE + 1;          // 3    post-sigmoid colour
+constexpr int R_DSIG = R_RGB + 3;            // 1    dL/d sigma_pre
+constexpr int R_DY = R_DSIG + 1;             // 3    dL/d colour pre-sigmoid
+constexpr int R_DPRE = R_DY + 3;             // 8 x 256   dL/d pre-activation of trunk layers
+constexpr int R_DPREC0 = R_DPRE + 8 * 256;   // 128
+constexpr int R_TOTAL = R_DPREC0 + 128;
+}  // namespace nerfb200

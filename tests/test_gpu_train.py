@@ -134,9 +134,9 @@ def test_adam_step_follows_reference_trainer(checkpoints):
     assert (num / den) ** 0.5 <= 0.05, (num / den) ** 0.5
 
 
-def test_train_step_bf16_mode_tensor_core_wgrad():
-    """BF16 mode (weight gradients on the tensor cores, bf16 operands): per-tensor relative error <= 1e-2
-    against the reference's fp32 autograd on the golden train step; loss unchanged (forward is fp32)."""
+def test_train_step_bf16_mode_tensor_cores():
+    """BF16 mode (forward and weight gradients on the tensor cores, bf16 operands, fp32 accumulation): loss within
+    0.5 % and per-tensor gradients within 3 % (relative L2) of the reference's fp32 autograd on the golden step."""
     from nerf_dbr_b200.host.trainer import B200TrainStep
     g = load_npz("golden_train.npz")
     ck = O.seeded_checkpoint(int(g["seed"]), float(g["density_gain"]))
@@ -150,7 +150,7 @@ def test_train_step_bf16_mode_tensor_core_wgrad():
     ro, rd, tgt = ro.reshape(-1, 3)[sel].cuda(), rd.reshape(-1, 3)[sel].cuda(), image.reshape(-1, 3)[sel].cuda()
     step = B200TrainStep(coarse, fine, 64, 128, mode=1)
     loss, _, _ = step(ro, rd, tgt, t_rand=torch.from_numpy(g["t_rand"]).cuda())
-    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert abs(float(loss) - float(g["loss"])) <= 5e-3 * float(g["loss"])
     rows = []
     for tag, m in (("coarse", coarse), ("fine", fine)):
         for name, p in m.named_parameters():
@@ -160,4 +160,4 @@ def test_train_step_bf16_mode_tensor_core_wgrad():
             rows.append((err, tag, name))
     rows.sort(reverse=True)
     print("bf16-mode worst relative gradient errors:", [(f"{e:.1e}", t, k) for e, t, k in rows[:5]])
-    assert rows[0][0] <= 1e-2, rows[0]
+    assert rows[0][0] <= 3e-2, rows[0]
