@@ -8,6 +8,7 @@ struct ChunkSrc { const float *w; int ld; int n0; int k0; int k_valid; int rows;
 // rows n0.. (n < rows), columns k0..k0+63; `extra` = one more row (the density head inside colour layer 0's chunks)
 
 __constant__ ChunkTable kPackTable = make_chunk_table();
+__constant__ ChunkTable kPackDgTable = make_dgrad_table();
 
 // source of bf16 chunk `ci` of the consumption-ordered stream (packed_layout.h)
 __device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int ci)
@@ -80,6 +81,30 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
         size_t off = chunk_offset(ci) + swz128((uint32_t)n, (uint32_t)unit * 8);
         *reinterpret_cast<uint4 *>(packed + B_OFFSET + off) = *reinterpret_cast<const uint4 *>(hi);
         *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
+    }
+
+    // ---- dgrad stream: chunk (g, half, kb), element (k, n) = W[64 kb + n][128 half + k] ----
+    const size_t dg_units = (size_t)kDgChunks * 128 * 8;
+    for (size_t uidx = tid; uidx < dg_units; uidx += nth) {
+        const int ci = (int)(uidx / 1024), k = (int)((uidx % 1024) / 8), unit = (int)(uidx % 8);
+        const ChunkInfo c = kPackDgTable.c[ci];
+        const int kin = 128 * c.half + k;                     // input feature of the layer = output of the dgrad GEMM
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = 64 * c.asrc + unit * 8 + j;         // output feature of the layer = K of the dgrad GEMM
+            float w = 0.f;
+            if (c.layer == 0) {
+                if (n < 128) w = p.color0_w[(size_t)n * 283 + kin];
+                else if (n == 128) w = p.density_w[kin];
+            } else {
+                const int l = 8 - c.layer;
+                w = p.layer_w[l][(size_t)n * (l == 4 ? 319 : 256) + kin];
+            }
+            v[j] = __float2bfloat16_rn(w);
+        }
+        *reinterpret_cast<uint4 *>(packed + B_DG_OFFSET + (size_t)ci * kChunkBytes + swz128((uint32_t)k, (uint32_t)unit * 8)) =
+            *reinterpret_cast<const uint4 *>(v);
     }
 }
 

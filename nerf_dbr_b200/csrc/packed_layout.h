@@ -125,11 +125,50 @@ constexpr ChunkTable make_chunk_table()
 }
 static_assert(make_chunk_table().c[kChunksPerTile - 1].layer == 8, "chunk table must fill exactly 64 entries");
 
+// ---- dgrad stream (training backward on the tensor cores) ---------------------------------
+// dX = dY . W per layer, run as the same N = 128-half / K-block schedule as the forward: 8 GEMMs per tile
+//   G0: dh7 = [dpre_c0 (128) | dsigma_pre (1)] . [W_c0[:, :256] ; w_sigma]      (K-blocks 0,1 = colour rows, 2 = the density row, 3 = 0)
+//   Gg: dh_{7-g} = dpre_{8-g} . W_{8-g}[:, :256]   for g = 1..7
+// chunk (g, half, kb) = [128 k x 64 n] bf16, element (k, n) = W[64 kb + n][128 half + k]: the transpose of the forward
+// operand, again pre-swizzled and stored in consumption order (8 chunks per GEMM, same pattern as a trunk layer).
+constexpr int kDgGemms = 8;
+constexpr int kDgChunks = kDgGemms * 8;                        // 64 x 16 KB = 1 MiB
+constexpr ChunkTable make_dgrad_table()
+{
+    ChunkTable t{};
+    int n = 0;
+    for (int g = 0; g < kDgGemms; ++g) {
+        const uint8_t G = (uint8_t)g;
+        const int begin = n;
+        t.c[n++] = ChunkInfo{G, 0, 0, 0};
+        t.c[n++] = ChunkInfo{G, 0, 1, 0};
+        t.c[n++] = ChunkInfo{G, 1, 0, 0};
+        t.c[n++] = ChunkInfo{G, 0, 2, 0};
+        t.c[n++] = ChunkInfo{G, 0, 3, 0};
+        t.c[n++] = ChunkInfo{G, 1, 1, 0};
+        t.c[n++] = ChunkInfo{G, 1, 2, 0};
+        t.c[n++] = ChunkInfo{G, 1, 3, 0};
+        for (int h = 0; h < 2; ++h) {
+            int first = -1, last = -1;
+            for (int i = begin; i < n; ++i)
+                if (t.c[i].half == h) { if (first < 0) first = i; last = i; }
+            t.c[first].flags |= 1;
+            t.c[last].flags |= 2;
+        }
+        for (int kb = 0; kb < 4; ++kb)
+            for (int i = begin; i < n; ++i)
+                if (t.c[i].asrc == kb) { t.c[i].flags |= 4; break; }
+    }
+    return t;
+}
+
 constexpr size_t B_OFFSET = ((F_END * 4 + 1023) / 1024) * 1024;   // byte offset of the bf16 region
 constexpr size_t B_BYTES = chunk_offset(kChunksPerTile);            // ~1 MiB
 // low-order bf16 stream for a split-precision mode follows (same layout)
 constexpr size_t B_LO_OFFSET = B_OFFSET + B_BYTES;
-constexpr size_t PACKED_BYTES = B_LO_OFFSET + B_BYTES;
+constexpr size_t B_DG_OFFSET = ((B_LO_OFFSET + B_BYTES + 1023) / 1024) * 1024;   // dgrad stream
+constexpr size_t B_DG_BYTES = (size_t)kDgChunks * kChunkBytes;
+constexpr size_t PACKED_BYTES = B_DG_OFFSET + B_DG_BYTES;
 
 // byte offset of element (n, k) inside one swizzled chunk
 __host__ __device__ constexpr uint32_t swz128(uint32_t n, uint32_t k)

@@ -16,8 +16,8 @@
 //
 // FP32 mode is the gradient parity reference on the device (relative error <= 5e-4 against the reference's
 // autograd).  BF16 mode runs the forward (the fused tcgen05 kernel's TRAIN variant, which stores the
-// activations it multiplies) and the weight-gradient GEMMs (train_tc.cu) on the tensor cores; the dgrad
-// chain on the tensor cores is the next step.
+// activations it multiplies), the dgrad chain (train_dgrad_tc.cu) and the weight-gradient GEMMs (train_tc.cu)
+// on the tensor cores; only the per-ray compositing backward and the two tiny head gradients stay on CUDA cores.
 #include <algorithm>
 #include "common.cuh"
 #include "simt_tile.cuh"
@@ -30,6 +30,7 @@ constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per S
 
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
                      float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream);
+int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
 int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream);
@@ -429,8 +430,17 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         }
         train_ray_kernel<<<std::min((a.n_rays + 7) / 8, sms * 8), 256, 0, stream>>>(a);
         if ((rc = launch_status())) return rc;
-        train_bwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
-        if ((rc = launch_status())) return rc;
+        if (tc) {
+            // dgrad chain on the tensor cores; the pad columns of the dpre rows must be zero for wgrad
+            const int n_smp = a.n_rays * n_samples;
+            if (a.ch != n_smp)
+                cudaMemset2DAsync(a.ws + (size_t)R_DPRE * a.ch + n_smp, (size_t)a.ch * sizeof(float), 0,
+                                  (size_t)(a.ch - n_smp) * sizeof(float), R_TOTAL - R_DPRE, stream);
+            if ((rc = dgrad_chain_tc(packed, a.ws, a.ch, n_smp, nullptr, stream))) return rc;
+        } else {
+            train_bwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
+            if ((rc = launch_status())) return rc;
+        }
         float *ws = a.ws;
         const size_t ch = a.ch;
         auto row = [&](int r) { return ws + (size_t)r * ch; };
