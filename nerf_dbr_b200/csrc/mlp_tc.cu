@@ -440,7 +440,7 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
 // ws_out (TRAIN): &workspace[first feature of this warp's 64][this row's sample] or nullptr; ws_ch = row pitch
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
-                                              float *ws_out = nullptr, int ws_ch = 0)
+                                              float *ws_out = nullptr, int ws_ch = 0, unsigned long long *mask_out = nullptr)
 {
     uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
@@ -452,11 +452,15 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
         bias_relu_pack(xb, pk + 16, bias_addr + 128);
         tmem_st32(t_cols, pk);                   // K-block: 64 bf16 in columns [0, 32) of this warp's range
         if (ws_out) {                            // exactly what the next layer multiplies: the bf16-rounded values
+            unsigned long long bits = 0ull;      // + the ReLU mask of these 64 activations for the dgrad chain
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 ws_out[(size_t)(2 * i) * ws_ch] = __uint_as_float(pk[i] << 16);
                 ws_out[(size_t)(2 * i + 1) * ws_ch] = __uint_as_float(pk[i] & 0xffff0000u);
+                bits |= (unsigned long long)((pk[i] & 0xffffu) != 0u) << (2 * i);
+                bits |= (unsigned long long)((pk[i] >> 16) != 0u) << (2 * i + 1);
             }
+            *mask_out = bits;
         }
     } else {
         uint32_t hi[16], lo[16];                 // hi halves in columns [0, 32), lo halves in [32, 64)
@@ -525,6 +529,8 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
 {
     float r[3] = {0.f, 0.f, 0.f};
     const uint32_t sg = tmem_ld1(t_row + 128);
+    unsigned long long *mask_c0 = reinterpret_cast<unsigned long long *>(ws + (size_t)R_MASKC0 * ws_ch);
+    unsigned int mbits[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
         uint32_t x[32];
@@ -548,11 +554,16 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
             r[2] = fmaf(v[0], w2.x, r[2]); r[2] = fmaf(v[1], w2.y, r[2]); r[2] = fmaf(v[2], w2.z, r[2]); r[2] = fmaf(v[3], w2.w, r[2]);
             if (col >= 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ws[(size_t)(R_C0H + 32 * g + 4 * i + j) * ws_ch + col] = v[j];
+                for (int j = 0; j < 4; ++j) {
+                    ws[(size_t)(R_C0H + 32 * g + 4 * i + j) * ws_ch + col] = v[j];
+                    mbits[g] |= (unsigned int)(v[j] > 0.f) << (4 * i + j);
+                }
             }
         }
     }
     if (col >= 0) {
+        mask_c0[col] = (unsigned long long)mbits[0] | ((unsigned long long)mbits[1] << 32);
+        mask_c0[(size_t)ws_ch + col] = (unsigned long long)mbits[2] | ((unsigned long long)mbits[3] << 32);
         ws[(size_t)R_SIGPRE * ws_ch + col] = __uint_as_float(sg) + __ldg(wf + F_BSIG);
 #pragma unroll
         for (int c = 0; c < 3; ++c) ws[(size_t)(R_RGB + c) * ws_ch + col] = 1.0f / (1.0f + expf(-(r[c] + __ldg(wf + F_BC1 + c))));
@@ -731,12 +742,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     tc_fence_after_sync();
                     if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
                     float *ws_out = nullptr;
+                    unsigned long long *mask_out = nullptr;
                     if (TRAIN) {
                         const int col = ws_col(a, row_info(a, tile_begin + t, row));
-                        if (col >= 0) ws_out = a.ws + (size_t)(R_H + layer * 256 + hh * 128 + 64 * w2) * a.ws_ch + col;
+                        if (col >= 0) {
+                            ws_out = a.ws + (size_t)(R_H + layer * 256 + hh * 128 + 64 * w2) * a.ws_ch + col;
+                            mask_out = reinterpret_cast<unsigned long long *>(a.ws + (size_t)R_MASK * a.ws_ch) +
+                                       (size_t)(layer * 4 + hh * 2 + w2) * a.ws_ch + col;
+                        }
                     }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, a.ws_ch);
+                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, a.ws_ch, mask_out);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();

@@ -149,6 +149,11 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
             for (int g = 0; g < kDgGemms; ++g) {
                 const int layer = 7 - g;                                   // dh of trunk layer `layer`
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
+                // the masks do not depend on the chain: fetch both halves' words before waiting for the accumulator
+                const unsigned long long *mrow = reinterpret_cast<const unsigned long long *>(a.ws + (size_t)R_MASK * ch) +
+                                                 (size_t)(layer * 4 + w2) * ch + col;
+                unsigned long long mbits[2] = {0ull, 0ull};
+                if (on) { mbits[0] = mrow[0]; mbits[1] = mrow[2 * ch]; }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     wait_bar(bar(B_ACCFULL + hh), g & 1, a.dbg, 5);
@@ -158,15 +163,14 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     uint32_t xa[32], xb[32], pk[32];
                     tmem_ld32(t_cols, xa);
                     tmem_ld32(t_cols + 32, xb);
-                    const float *hm = a.ws + (size_t)(R_H + layer * 256 + n0) * ch + col;
-                    float *dp = a.ws + (size_t)(R_DPRE + layer * 256 + n0) * ch + col;
                     tmem_ld_wait();
+                    const unsigned long long m = on ? mbits[hh] : 0ull;      // ReLU mask of these 64 activations
+                    float *dp = a.ws + (size_t)(R_DPRE + layer * 256 + n0) * ch + col;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        float v0 = 0.f, u0 = 0.f;
+                        const float v0 = (m >> i) & 1ull ? __uint_as_float(xa[i]) : 0.f;
+                        const float u0 = (m >> (32 + i)) & 1ull ? __uint_as_float(xb[i]) : 0.f;
                         if (on) {
-                            v0 = hm[(size_t)(i) * ch] > 0.f ? __uint_as_float(xa[i]) : 0.f;
-                            u0 = hm[(size_t)(32 + i) * ch] > 0.f ? __uint_as_float(xb[i]) : 0.f;
                             dp[(size_t)(i) * ch] = v0;
                             dp[(size_t)(32 + i) * ch] = u0;
                         }
@@ -201,10 +205,13 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
             const int col = (tile_begin + t) * 128 + row;
             const bool on = col < a.n_samples_total;
             float dy[3] = {0.f, 0.f, 0.f}, dsig = 0.f;
+            unsigned long long mc0[2] = {0ull, 0ull};
             if (on) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) dy[c] = a.ws[(size_t)(R_DY + c) * ch + col];
                 dsig = a.ws[(size_t)R_DSIG * ch + col];
+                const unsigned long long *mp = reinterpret_cast<const unsigned long long *>(a.ws + (size_t)R_MASKC0 * ch);
+                mc0[0] = mp[col]; mc0[1] = mp[ch + col];
             }
             if (t > 0) wait_bar(bar(B_R1FREE), (t - 1) & 1, a.dbg, 8);
             tc_fence_after_sync();
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int n = 64 * kb + 4 * i + j;
-                            if (!(a.ws[(size_t)(R_C0H + n) * ch + col] > 0.f)) v[j] = 0.f;
+                            if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
                             a.ws[(size_t)(R_DPREC0 + n) * ch + col] = v[j];
                         }
                     }

@@ -12,5 +12,9 @@ constexpr int R_DSIG = R_RGB + 3;            // 1    dL/d sigma_pre
 constexpr int R_DY = R_DSIG + 1;             // 3    dL/d colour pre-sigmoid
 constexpr int R_DPRE = R_DY + 3;             // 8 x 256   dL/d pre-activation of trunk layers
 constexpr int R_DPREC0 = R_DPRE + 8 * 256;   // 128
-constexpr int R_TOTAL = R_DPREC0 + 128;
+// ReLU masks written by the tensor-core forward (bit j of word (layer, part) = activation 64*part + j > 0), so the
+// dgrad chain reads 8 bytes per thread and half instead of 64 strided floats: uint64 [(layer*4 + part)][ch]
+constexpr int R_MASK = R_DPREC0 + 128;       // 8 layers x 4 parts x 2 floats (one uint64 per sample)
+constexpr int R_MASKC0 = R_MASK + 64;        // colour layer 0: 2 parts x 2 floats
+constexpr int R_TOTAL = R_MASKC0 + 4;
 }  // namespace nerfb200

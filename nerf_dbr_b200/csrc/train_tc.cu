@@ -157,17 +157,24 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int split
     }
 }
 
-// dbias[n] += sum_s A[n][s]; one warp per row
-__global__ void rowsum_kernel(const float *__restrict__ A, int rows, int ch, float *__restrict__ dbias)
+// dbias[n] += sum_s A[n][s]; one block per row (a row is up to 1 MB: the whole GPU has to pull)
+__global__ void __launch_bounds__(256) rowsum_kernel(const float *__restrict__ A, int rows, int ch, float *__restrict__ dbias)
 {
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = blockIdx.x * warps + warp; r < rows; r += gridDim.x * warps) {
-        const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)r * ch);
-        float s = 0.f;
-        for (int i = lane; i < ch / 4; i += 32) { float4 v = __ldg(p + i); s += (v.x + v.y) + (v.z + v.w); }
+    __shared__ float part[8];
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)r * ch);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < ch / 4; i += 256) { float4 v = __ldg(p + i); s += (v.x + v.y) + (v.z + v.w); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) dbias[r] += s;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i];
+        dbias[r] += t;
     }
 }
 
@@ -194,7 +201,7 @@ int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int c
     wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.rows_b, rows_b_valid, dW, ld, col_off);
     if ((rc = launch_status())) return rc;
     if (dbias) {
-        wg::rowsum_kernel<<<(rows_a + 7) / 8, 256, 0, stream>>>(A, rows_a, ch, dbias);
+        wg::rowsum_kernel<<<rows_a, 256, 0, stream>>>(A, rows_a, ch, dbias);
         rc = launch_status();
     }
     return rc;
