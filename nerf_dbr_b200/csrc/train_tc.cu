@@ -97,17 +97,36 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
             if (c >= 2) wait(bar(B_EMPTY + s), ((c >> 1) - 1) & 1);
             const size_t s0 = (size_t)(c_begin + c) * 64;
             uint8_t *ta = sm + s * kStage, *tb = ta + kTileA;
-            for (int u = lt; u < units_a + units_b; u += n_lt) {
-                const bool is_a = u < units_a;
-                const int v = is_a ? u : u - units_a;
-                const int row = v >> 3, cu = v & 7;
-                uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                if (is_a || row < a.rows_b_valid) {
-                    const float4 *src = reinterpret_cast<const float4 *>((is_a ? a.A : a.B) + (size_t)row * a.ch + s0 + cu * 8);
-                    const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
-                    packed = make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
+            // batches of 4 units per thread: 8 independent 16-byte loads in flight before the first conversion
+            // (the kernel is HBM-bound; a load-convert-store loop leaves the memory system idle)
+            for (int u0 = lt; u0 < units_a + units_b; u0 += 4 * n_lt) {
+                float4 x[4][2];
+                bool live[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int u = u0 + b * n_lt;
+                    const bool is_a = u < units_a;
+                    const int v = is_a ? u : u - units_a;
+                    const int row = v >> 3, cu = v & 7;
+                    live[b] = u < units_a + units_b && (is_a || row < a.rows_b_valid);
+                    if (live[b]) {
+                        const float4 *src = reinterpret_cast<const float4 *>((is_a ? a.A : a.B) + (size_t)row * a.ch + s0 + cu * 8);
+                        x[b][0] = __ldg(src); x[b][1] = __ldg(src + 1);
+                    }
                 }
-                *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = packed;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int u = u0 + b * n_lt;
+                    if (u >= units_a + units_b) continue;
+                    const bool is_a = u < units_a;
+                    const int v = is_a ? u : u - units_a;
+                    const int row = v >> 3, cu = v & 7;
+                    uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+                    if (live[b])
+                        packed = make_uint4(pack_bf16(x[b][0].x, x[b][0].y), pack_bf16(x[b][0].z, x[b][0].w),
+                                            pack_bf16(x[b][1].x, x[b][1].y), pack_bf16(x[b][1].z, x[b][1].w));
+                    *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = packed;
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
