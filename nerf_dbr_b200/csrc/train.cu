@@ -31,6 +31,8 @@ constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per S
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
                      float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream);
 int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, cudaStream_t stream);
+int wgrad_skinny(const float *A, int rows_a, const float *B, int rows_b, int ch, float *dW, int ld, float *dbias,
+                 cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
 int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream);
@@ -448,6 +450,8 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         float *scratch = ws + (size_t)R_TOTAL * ch;
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
+            if (tc && rows_a <= 4 && col_off == 0)
+                return wgrad_skinny(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, const_cast<float *>(db), stream);
             if (tc && rows_a >= 128)
                 return wgrad_tc(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off, const_cast<float *>(db),
                                 scratch, kWgradSplits, stream);

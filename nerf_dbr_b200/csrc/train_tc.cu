@@ -35,6 +35,7 @@ struct Args {
     int rows_b_valid;
     int ch;                                      // samples (multiple of 64)
     float *partial;                              // [gridDim.x][rows_a][rows_b]
+    float *dbias;                                // optional: dbias[n] += sum_s A[n][s] (fp32, from the loader's registers)
 };
 
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
         // ---------------- loaders: fp32 [row][sample] -> bf16 swizzled K-major tiles
         const int lt = (warp - 4) * 32 + lane, n_lt = kLoaderWarps * 32;
         const int units_a = a.rows_a * 8, units_b = a.rows_b * 8;      // 16-byte units (8 samples) per 64-sample slab
+        // a thread meets the same A rows in every slab (unit index -> row is slab-independent): bias partial sums
+        // ride in registers, one per batch slot
+        float bsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (int c = 0; c < my_chunks; ++c) {
             const int s = c & 1;
             if (c >= 2) wait(bar(B_EMPTY + s), ((c >> 1) - 1) & 1);
@@ -99,7 +103,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
             uint8_t *ta = sm + s * kStage, *tb = ta + kTileA;
             // batches of 4 units per thread: 8 independent 16-byte loads in flight before the first conversion
             // (the kernel is HBM-bound; a load-convert-store loop leaves the memory system idle)
-            for (int u0 = lt; u0 < units_a + units_b; u0 += 4 * n_lt) {
+            int batch = 0;
+            for (int u0 = lt; u0 < units_a + units_b; u0 += 4 * n_lt, ++batch) {
                 float4 x[4][2];
                 bool live[4];
 #pragma unroll
@@ -122,15 +127,28 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                     const int v = is_a ? u : u - units_a;
                     const int row = v >> 3, cu = v & 7;
                     uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                    if (live[b])
+                    if (live[b]) {
                         packed = make_uint4(pack_bf16(x[b][0].x, x[b][0].y), pack_bf16(x[b][0].z, x[b][0].w),
                                             pack_bf16(x[b][1].x, x[b][1].y), pack_bf16(x[b][1].z, x[b][1].w));
+                        if (is_a && batch < 2)
+                            bsum[batch][b] += ((x[b][0].x + x[b][0].y) + (x[b][0].z + x[b][0].w)) +
+                                              ((x[b][1].x + x[b][1].y) + (x[b][1].z + x[b][1].w));
+                    }
                     *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = packed;
                 }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_FULL + s));
+        }
+        if (a.dbias) {                                  // units_a <= 2048 = 2 batches of 4 x 384 threads (less 1024)
+#pragma unroll
+            for (int batch = 0; batch < 2; ++batch)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int u = lt + (batch * 4 + b) * n_lt;
+                    if (u < units_a && bsum[batch][b] != 0.f) atomicAdd(a.dbias + (u >> 3), bsum[batch][b]);
+                }
         }
         // ---------------- epilogue: accumulators -> this CTA's partial
         if (my_chunks > 0) {
@@ -197,7 +215,50 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const float *__restrict__ A
     }
 }
 
+// Skinny weight gradients (density head: 1 output row; colour layer 1: 3): dW[a][k] += sum_s A[a][s] B[k][s],
+// dbias[a] += sum_s A[a][s].  One block per input feature k streams B's row once; A (<= 4 rows) stays in L2.
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, const float *__restrict__ B,
+                                                           int rows_b, int ch, float *__restrict__ dW, int ld,
+                                                           float *__restrict__ dbias)
+{
+    __shared__ float part[8][5];
+    const int k = blockIdx.x;                      // k == rows_b: the bias block (B row of ones)
+    const float4 *bp = k < rows_b ? reinterpret_cast<const float4 *>(B + (size_t)k * ch) : nullptr;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < ch / 4; i += 256) {
+        const float4 b = bp ? __ldg(bp + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r < rows_a) {
+                const float4 av = __ldg(reinterpret_cast<const float4 *>(A + (size_t)r * ch) + i);
+                s[r] += (av.x * b.x + av.y * b.y) + (av.z * b.z + av.w * b.w);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) part[threadIdx.x >> 5][r] = s[r];
+    __syncthreads();
+    if (threadIdx.x < rows_a) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        if (k < rows_b) dW[(size_t)threadIdx.x * ld + k] += t;
+        else if (dbias) dbias[threadIdx.x] += t;
+    }
+}
+
 }  // namespace wg
+
+int wgrad_skinny(const float *A, int rows_a, const float *B, int rows_b, int ch, float *dW, int ld, float *dbias,
+                 cudaStream_t stream)
+{
+    wg::wgrad_skinny_kernel<<<rows_b + 1, 256, 0, stream>>>(A, rows_a, B, rows_b, ch, dW, ld, dbias);
+    return launch_status();
+}
 
 size_t wgrad_tc_scratch_bytes(int splits) { return (size_t)splits * 256 * 256 * sizeof(float); }
 
@@ -208,7 +269,7 @@ int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int c
     wg::Args a = {};
     a.A = A; a.rows_a = rows_a; a.B = B; a.rows_b_valid = rows_b_valid;
     a.rows_b = (rows_b_valid + 15) / 16 * 16;
-    a.ch = ch; a.partial = scratch;
+    a.ch = ch; a.partial = scratch; a.dbias = dbias;
     const int n_chunks = ch / 64;
     if (splits > n_chunks) splits = n_chunks;
     cudaError_t e = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
@@ -219,10 +280,6 @@ int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int c
     const int total = rows_a * rows_b_valid;
     wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.rows_b, rows_b_valid, dW, ld, col_off);
     if ((rc = launch_status())) return rc;
-    if (dbias) {
-        wg::rowsum_kernel<<<rows_a, 256, 0, stream>>>(A, rows_a, ch, dbias);
-        rc = launch_status();
-    }
     return rc;
 }
 
