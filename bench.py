@@ -218,13 +218,15 @@ def run_train(args):
         emit({"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+Adam", "value": n_rays / (ms * 1e-3),
               "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-              "dtype": "bf16 wgrad / f32 forward+dgrad" if args.precision == "bf16" else "f32", "data": "synthetic",
+              "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
               "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
                          "loss_last": float(loss)},
               "gpu_launches": int(ops.launch_count() - n0),
               "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peaks()["bf16_tflops"],
                            "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peaks()["bf16_tflops"], "traffic": None,
-                           "note": "FP32 CUDA-core kernels; tensor-core training kernels are the next step"}})
+                           "note": ("forward, dgrad chain and wgrad on tcgen05 (bf16 operands, fp32 accumulate); activations "
+                                    "round-trip HBM between the three phases" if args.precision == "bf16"
+                                    else "FP32 CUDA-core kernels (gradient parity mode)")}})
     if world > 1:
         dist.destroy_process_group()
 
