@@ -127,7 +127,6 @@ constexpr int kTraceTiles = 6;
 //   0 MMA: first chunk of the layer issued   1 MMA: half 0 committed   2 MMA: last half committed
 //   3 EPI(warp 4): half 0 acc_full seen   4 EPI: half 0 a_ready arrive   5 EPI: layer done
 //   6 EPI: last half acc_full seen
-#define TC_TRACE(tile, layer, slot) do { if (a.trace && blockIdx.x == 0 && (tile) < kTraceTiles) a.trace[((tile) * 9 + (layer)) * 8 + (slot)] = clock64(); } while (0)
 
 constexpr long long kTimeoutCycles = 4000000000LL;
 
@@ -300,11 +299,10 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
 // ------------------------------------------------------------------------------------------
 // back: sigmoid / relu heads, alpha, segmented transmittance scan, weighted sums, output
 template <int SRC>
-__device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int fb, int row, float step,
-                               const float *__restrict__ wf, uint32_t bar_fin_empty, float sig_pre, const float (&ypre)[3])
+__device__ void composite_tile(const Args &a, uint8_t *sm, int tile, int row, float step,
+                               const float *__restrict__ wf, float sig_pre, const float (&ypre)[3])
 {
     const int lane = row & 31, warp = row >> 5;
-    (void)fb; (void)bar_fin_empty;
 
     RowInfo ri = row_info(a, tile, row);
     float sigma = fmaxf(sig_pre + __ldg(wf + F_BSIG), 0.f);
@@ -774,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         if (my_tiles > 0) produce(0);
         for (int t = 0; t < my_tiles; ++t) {
             if (t + 1 < my_tiles) produce(t + 1);
-            const int fb = t & 1, pb = t & 1;           // per-ray bias buffers always alternate
+            const int pb = t & 1;                       // per-ray bias buffers always alternate
             // colour layer 0's epilogue: this thread's accumulator row straight from TMEM
             wait_bar(bar(B_ACCC0), t & 1, a.dbg, 11);
             tc_fence_after_sync();
@@ -787,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                 float ypre[3], sig_pre;
                 color_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
                           bar(B_C0FREE), lane, ypre[0], ypre[1], ypre[2], sig_pre);
-                composite_tile<SRC>(a, sm, tile_begin + t, fb, row, step, wf, 0, sig_pre, ypre);
+                composite_tile<SRC>(a, sm, tile_begin + t, row, step, wf, sig_pre, ypre);
             }
         }
     }

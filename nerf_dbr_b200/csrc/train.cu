@@ -1,9 +1,10 @@
-// Training step, FP32 mode: forward + backward of ONE network's photometric-MSE term
+// Training step: forward + backward of ONE network's photometric-MSE term (host entry point for both modes; the
+// FP32-mode kernels live here, the BF16-mode tensor-core kernels in mlp_tc.cu / train_dgrad_tc.cu / train_tc.cu)
 //   loss_term = mean_{R x 3} (C - target)^2,   C = composite(MLP(points on rays))
 // reference: NeRFTrainer.train_step / _render_rays / _query_network (src/training/trainer.py:83-138,
 // 294-351), VolumeRenderer.volume_render (src/utils/rendering.py:102-143); backward math: SURVEY App. B.
 //
-// Rays are processed in chunks (bounded caller-owned workspace).  Per chunk:
+// Rays are processed in chunks (bounded caller-owned workspace).  Per chunk, FP32 mode:
 //   1. train_fwd_kernel   64-sample tiles: encode, 8x256 trunk, heads; every layer's activations are
 //                         stored K-major ([feature][sample]) for the backward
 //   2. train_ray_kernel   one warp per ray: compositing forward, loss, dL/dC, compositing backward

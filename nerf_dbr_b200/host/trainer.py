@@ -43,3 +43,27 @@ class B200TrainStep:
         if allreduce:
             loss = allreduce_sum_([p.grad for p in self.parameters()], extra=loss)   # one 4.24 MB sum over NVLink
         return loss, rgb_c, rgb_f
+
+
+def save_checkpoint(path: str, step: B200TrainStep, optimizer, scheduler=None, config=None, train_losses=(),
+                    val_losses=()) -> None:
+    """Write a checkpoint in the reference's format (NeRFTrainer.save_checkpoint, src/training/trainer.py:374-388):
+    the renderers read 'coarse_model' / 'fine_model' (base_renderer.py:47-48), the reference trainer resumes from
+    the rest."""
+    torch.save({"coarse_model": {k: v.detach().cpu() for k, v in step.coarse.state_dict().items()},
+                "fine_model": {k: v.detach().cpu() for k, v in step.fine.state_dict().items()},
+                "optimizer": optimizer.state_dict(),
+                "scheduler": scheduler.state_dict() if scheduler is not None else {},
+                "config": dict(config or {}), "train_losses": list(train_losses), "val_losses": list(val_losses)}, path)
+
+
+def load_checkpoint(path: str, step: B200TrainStep, optimizer=None, scheduler=None):
+    """Counterpart of NeRFTrainer.load_checkpoint (trainer.py:390-402); returns (train_losses, val_losses)."""
+    ck = torch.load(path, map_location=next(step.coarse.parameters()).device, weights_only=False)
+    step.coarse.load_state_dict(ck["coarse_model"])
+    step.fine.load_state_dict(ck["fine_model"])
+    if optimizer is not None and ck.get("optimizer"):
+        optimizer.load_state_dict(ck["optimizer"])
+    if scheduler is not None and ck.get("scheduler"):
+        scheduler.load_state_dict(ck["scheduler"])
+    return ck.get("train_losses", []), ck.get("val_losses", [])

@@ -205,3 +205,43 @@ def test_train_step_bf16_mode_tensor_cores():
     print("bf16 mode vs reference fp32 autograd:", [(f"{e:.1e}", t, k) for e, t, k in rows_ref[:4]])
     assert rows_emu[0][0] <= 2e-2, rows_emu[0]
     assert rows_ref[0][0] <= 0.15, rows_ref[0]
+
+
+def test_checkpoint_round_trip_reference_format(tmp_path, checkpoints, poses):
+    """A checkpoint written after CUDA training steps has the reference's keys (trainer.py:374-388), loads through the
+    renderer's SharedNeRFModel path (base_renderer.py:42-48) and resumes training bit-identically."""
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host.trainer import B200TrainStep, load_checkpoint, save_checkpoint
+    ck = O.seeded_checkpoint(5, 30.0)
+    coarse, fine = models_from(ck)
+    step = B200TrainStep(coarse, fine, 32, 64)
+    opt = torch.optim.Adam(step.parameters(), lr=5e-4)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.1 ** (1 / 250000))
+    ro, rd = O.camera_rays(poses["generic"], 16, 8)
+    ro, rd = ro.reshape(-1, 3).cuda(), rd.reshape(-1, 3).cuda()
+    g = torch.Generator().manual_seed(3)
+    tgt, tr = torch.rand(128, 3, generator=g).cuda(), torch.rand(128, 32, generator=g).cuda()
+    losses = []
+    for _ in range(2):
+        loss, _, _ = step(ro, rd, tgt, t_rand=tr)
+        opt.step(); sched.step(); losses.append(float(loss))
+    path = str(tmp_path / "checkpoint_epoch_2.pth")
+    save_checkpoint(path, step, opt, sched, {"n_rays": 128}, losses, [])
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) == {"coarse_model", "fine_model", "optimizer", "scheduler", "config", "train_losses", "val_losses"}
+    r = nb.B200Renderer("fp32")
+    r.setup(path)                                            # the renderer-side loader
+    rgb, _ = r.render_image(poses["generic"], (16, 8), 16)
+    ref, _ = O.render_image({k: v.cpu() for k, v in fine.state_dict().items()}, poses["generic"], 16, 8, 16)
+    assert (rgb.cpu() - ref).abs().max() <= 1e-4
+    # resume: a fresh trainer loaded from the file takes the same next step
+    c2, f2 = models_from(O.seeded_checkpoint(1))
+    step2 = B200TrainStep(c2, f2, 32, 64)
+    opt2 = torch.optim.Adam(step2.parameters(), lr=5e-4)
+    tl, _ = load_checkpoint(path, step2, opt2)
+    assert tl == losses
+    l1, _, _ = step(ro, rd, tgt, t_rand=tr); opt.step()
+    l2, _, _ = step2(ro, rd, tgt, t_rand=tr); opt2.step()
+    assert float(l1) == float(l2)
+    for a, b in zip(step.parameters(), step2.parameters()):
+        assert torch.equal(a, b)
