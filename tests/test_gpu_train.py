@@ -242,6 +242,8 @@ def test_checkpoint_round_trip_reference_format(tmp_path, checkpoints, poses):
     assert tl == losses
     l1, _, _ = step(ro, rd, tgt, t_rand=tr); opt.step()
     l2, _, _ = step2(ro, rd, tgt, t_rand=tr); opt2.step()
-    assert float(l1) == float(l2)
-    for a, b in zip(step.parameters(), step2.parameters()):
-        assert torch.equal(a, b)
+    # fp32 atomics (loss and gradient accumulation) make a step reproducible to rounding, not to the bit
+    assert abs(float(l1) - float(l2)) <= 1e-6 * float(l1)
+    num = sum(float((a - b).double().norm() ** 2) for a, b in zip(step.parameters(), step2.parameters()))
+    den = sum(float(a.double().norm() ** 2) for a in step.parameters())
+    assert (num / den) ** 0.5 <= 1e-5
