@@ -165,24 +165,24 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     tmem_ld32(t_cols + 32, xb);
                     tmem_ld_wait();
                     const unsigned long long m = on ? mbits[hh] : 0ull;      // ReLU mask of these 64 activations
-                    float *dp = a.ws + (size_t)(R_DPRE + layer * 256 + n0) * ch + col;
+                    unsigned short *dp = reinterpret_cast<unsigned short *>(a.ws) + (size_t)(R_DPRE + layer * 256 + n0) * ch + col;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float v0 = (m >> i) & 1ull ? __uint_as_float(xa[i]) : 0.f;
-                        const float u0 = (m >> (32 + i)) & 1ull ? __uint_as_float(xb[i]) : 0.f;
+                    for (int i = 0; i < 16; ++i) {
+                        // bf16 pairs: the values wgrad multiplies are exactly the ones the next GEMM of the chain sees
+                        const float a0 = (m >> (2 * i)) & 1ull ? __uint_as_float(xa[2 * i]) : 0.f;
+                        const float a1 = (m >> (2 * i + 1)) & 1ull ? __uint_as_float(xa[2 * i + 1]) : 0.f;
+                        const float b0 = (m >> (32 + 2 * i)) & 1ull ? __uint_as_float(xb[2 * i]) : 0.f;
+                        const float b1 = (m >> (33 + 2 * i)) & 1ull ? __uint_as_float(xb[2 * i + 1]) : 0.f;
+                        pk[i] = pack_bf16(a0, a1);
+                        pk[16 + i] = pack_bf16(b0, b1);
                         if (on) {
-                            dp[(size_t)(i) * ch] = v0;
-                            dp[(size_t)(32 + i) * ch] = u0;
+                            dp[(size_t)(2 * i) * ch] = (unsigned short)(pk[i] & 0xffffu);
+                            dp[(size_t)(2 * i + 1) * ch] = (unsigned short)(pk[i] >> 16);
+                            dp[(size_t)(32 + 2 * i) * ch] = (unsigned short)(pk[16 + i] & 0xffffu);
+                            dp[(size_t)(33 + 2 * i) * ch] = (unsigned short)(pk[16 + i] >> 16);
                         }
-                        xa[i] = __float_as_uint(v0);
-                        xb[i] = __float_as_uint(u0);
                     }
                     if (g < kDgGemms - 1) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            pk[i] = pack_bf16(__uint_as_float(xa[2 * i]), __uint_as_float(xa[2 * i + 1]));
-                            pk[16 + i] = pack_bf16(__uint_as_float(xb[2 * i]), __uint_as_float(xb[2 * i + 1]));
-                        }
                         tmem_st32(t_cols, pk);
                         tmem_st_wait();
                         tc_fence_before_sync();
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         for (int j = 0; j < 4; ++j) {
                             const int n = 64 * kb + 4 * i + j;
                             if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
-                            a.ws[(size_t)(R_DPREC0 + n) * ch + col] = v[j];
+                            reinterpret_cast<__nv_bfloat16 *>(a.ws)[(size_t)(R_DPREC0 + n) * ch + col] = __float2bfloat16_rn(v[j]);
                         }
                     }
                     pk[2 * i] = pack_bf16(v[0], v[1]);

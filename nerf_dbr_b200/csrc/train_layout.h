@@ -1,6 +1,9 @@
 // Training workspace layout shared by train.cu (FP32 kernels), train_tc.cu and the TRAIN variant of the fused
 // tensor-core kernel (mlp_tc.cu): [row][ch] fp32, K-major for the weight-gradient GEMMs (sample contiguous).
 #pragma once
+// BF16 mode keeps the big operand rows (R_PE, R_H, R_C0H, R_DE, R_DPRE, R_DPREC0) as bf16 with the SAME row numbers and
+// pitch `ch` elements, i.e. row r at byte r * ch * 2 of the same buffer (they end at byte 8912 ch, below the first fp32
+// row it still uses, R_SIGPRE at byte 9088 ch); the small per-sample rows and the masks stay fp32 / uint64.
 namespace nerfb200 {
 constexpr int R_PE = 0;                      // 64   encoded position (row 63 = 0)
 constexpr int R_H = R_PE + 64;               // 8 x 256   post-ReLU trunk activations

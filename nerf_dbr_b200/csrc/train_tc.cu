@@ -2,8 +2,8 @@
 //
 // wgrad_tc_kernel -- dW[n][k] = sum_s dY[n][s] X[k][s] for one parameter tensor, as a tcgen05 GEMM with
 // M = n (128 or 256 output features), N = k (up to 256 input features), K = samples.  Both operands sit in
-// the training workspace K-major ([feature][sample], fp32); loader warps convert 64-sample slabs to bf16 and
-// write them straight into the 128B-swizzled K-major shared-memory tiles the MMA reads (A: [rows_a x 64],
+// the training workspace K-major ([feature][sample], bf16 -- exactly the values the forward and the dgrad chain
+// multiplied); loader warps copy 64-sample slabs straight into the 128B-swizzled K-major shared-memory tiles the MMA reads (A: [rows_a x 64],
 // B: [rows_b x 64], two stages); the fp32 accumulators of the whole 256 x 256 tensor fill the 512 TMEM
 // columns.  The sample range is split over CTAs; each writes its partial to scratch and
 // wgrad_reduce_kernel folds the partials into the caller's gradient tensor (no atomics).
@@ -30,8 +30,8 @@ constexpr uint32_t kSmem = SM_TMEM + 16 + 1024;
 enum { B_FULL = 0, B_EMPTY = 2, B_DONE = 4 };
 
 struct Args {
-    const float *A; int rows_a;                  // 128 or 256
-    const float *B; int rows_b;                  // padded to a multiple of 16, <= 256; rows >= rows_b_valid read as 0
+    const __nv_bfloat16 *A; int rows_a;          // 128 or 256
+    const __nv_bfloat16 *B; int rows_b;                  // padded to a multiple of 16, <= 256; rows >= rows_b_valid read as 0
     int rows_b_valid;
     int ch;                                      // samples (multiple of 64)
     float *partial;                              // [gridDim.x][rows_a][rows_b]
@@ -105,19 +105,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
             // (the kernel is HBM-bound; a load-convert-store loop leaves the memory system idle)
             int batch = 0;
             for (int u0 = lt; u0 < units_a + units_b; u0 += 4 * n_lt, ++batch) {
-                float4 x[4][2];
-                bool live[4];
+                uint4 x[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const int u = u0 + b * n_lt;
                     const bool is_a = u < units_a;
                     const int v = is_a ? u : u - units_a;
                     const int row = v >> 3, cu = v & 7;
-                    live[b] = u < units_a + units_b && (is_a || row < a.rows_b_valid);
-                    if (live[b]) {
-                        const float4 *src = reinterpret_cast<const float4 *>((is_a ? a.A : a.B) + (size_t)row * a.ch + s0 + cu * 8);
-                        x[b][0] = __ldg(src); x[b][1] = __ldg(src + 1);
-                    }
+                    x[b] = make_uint4(0u, 0u, 0u, 0u);
+                    if (u < units_a + units_b && (is_a || row < a.rows_b_valid))
+                        x[b] = __ldg(reinterpret_cast<const uint4 *>((is_a ? a.A : a.B) + (size_t)row * a.ch + s0 + cu * 8));
                 }
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
@@ -126,15 +123,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                     const bool is_a = u < units_a;
                     const int v = is_a ? u : u - units_a;
                     const int row = v >> 3, cu = v & 7;
-                    uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                    if (live[b]) {
-                        packed = make_uint4(pack_bf16(x[b][0].x, x[b][0].y), pack_bf16(x[b][0].z, x[b][0].w),
-                                            pack_bf16(x[b][1].x, x[b][1].y), pack_bf16(x[b][1].z, x[b][1].w));
-                        if (is_a && batch < 2)
-                            bsum[batch][b] += ((x[b][0].x + x[b][0].y) + (x[b][0].z + x[b][0].w)) +
-                                              ((x[b][1].x + x[b][1].y) + (x[b][1].z + x[b][1].w));
+                    *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = x[b];
+                    if (is_a && batch < 2) {
+                        const uint32_t w[4] = {x[b].x, x[b].y, x[b].z, x[b].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bsum[batch][b] += __uint_as_float(w[j] << 16) + __uint_as_float(w[j] & 0xffff0000u);
                     }
-                    *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = packed;
                 }
             }
             fence_proxy_async_smem();
@@ -217,16 +211,21 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const float *__restrict__ A
 
 // Skinny weight gradients (density head: 1 output row; colour layer 1: 3): dW[a][k] += sum_s A[a][s] B[k][s],
 // dbias[a] += sum_s A[a][s].  One block per input feature k streams B's row once; A (<= 4 rows) stays in L2.
-__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, const float *__restrict__ B,
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, const __nv_bfloat16 *__restrict__ B,
                                                            int rows_b, int ch, float *__restrict__ dW, int ld,
                                                            float *__restrict__ dbias)
 {
     __shared__ float part[8][5];
     const int k = blockIdx.x;                      // k == rows_b: the bias block (B row of ones)
-    const float4 *bp = k < rows_b ? reinterpret_cast<const float4 *>(B + (size_t)k * ch) : nullptr;
+    const uint2 *bp = k < rows_b ? reinterpret_cast<const uint2 *>(B + (size_t)k * ch) : nullptr;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < ch / 4; i += 256) {
-        const float4 b = bp ? __ldg(bp + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 b = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (bp) {
+            const uint2 r = __ldg(bp + i);
+            b = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                            __uint_as_float(r.y & 0xffff0000u));
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
             if (r < rows_a) {
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restri
 
 }  // namespace wg
 
-int wgrad_skinny(const float *A, int rows_a, const float *B, int rows_b, int ch, float *dW, int ld, float *dbias,
+int wgrad_skinny(const float *A, int rows_a, const __nv_bfloat16 *B, int rows_b, int ch, float *dW, int ld, float *dbias,
                  cudaStream_t stream)
 {
     wg::wgrad_skinny_kernel<<<rows_b + 1, 256, 0, stream>>>(A, rows_a, B, rows_b, ch, dW, ld, dbias);
@@ -263,7 +262,7 @@ int wgrad_skinny(const float *A, int rows_a, const float *B, int rows_b, int ch,
 size_t wgrad_tc_scratch_bytes(int splits) { return (size_t)splits * 256 * 256 * sizeof(float); }
 
 // dW (+)= A^T-by-B over the chunk's samples on the tensor cores; bias row sums on CUDA cores.
-int wgrad_tc(const float *A, int rows_a, const float *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
+int wgrad_tc(const __nv_bfloat16 *A, int rows_a, const __nv_bfloat16 *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream)
 {
     wg::Args a = {};
