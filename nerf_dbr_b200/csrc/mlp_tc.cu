@@ -235,9 +235,9 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
     if (TRAIN) {                                           // the bf16 values the MMA sees, [feature][sample] for wgrad
         const int col = ws_col(a, ri);
         if (col >= 0) {
-            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws) + (size_t)R_PE * a.ws_ch + col;
+            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws);
 #pragma unroll
-            for (int f = 0; f < 64; ++f) p[(size_t)f * a.ws_ch] = __float2bfloat16_rn(feat[f]);
+            for (int f = 0; f < 64; ++f) p[big_off(R_PE + f, col)] = __float2bfloat16_rn(feat[f]);
         }
     }
     const uint32_t pe_row = smem_u32(sm + SM_PE + pe_buf * 16384 + row * 128);
@@ -288,9 +288,9 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
         const int col = ws_col(a, ri);
         if (col >= 0) {
             const int q = a.tiles_per_ray == 1 ? (row >> a.s_pad_log2) : 0;
-            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws) + (size_t)R_DE * a.ws_ch + col;
+            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws);
 #pragma unroll
-            for (int f = 0; f < kDirFeat; ++f) p[(size_t)f * a.ws_ch] = __float2bfloat16_rn(de[q * 32 + f]);
+            for (int f = 0; f < 32; ++f) p[big_off(R_DE + f, col)] = __float2bfloat16_rn(f < kDirFeat ? de[q * 32 + f] : 0.f);
         }
     }
     named_bar_sync(1, 128);          // de[] is rewritten by the next produce
@@ -435,10 +435,12 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
     }
 }
 
-// ws_out (TRAIN): &workspace[first feature of this warp's 64][this row's sample] (bf16 rows) or nullptr; ws_ch = row pitch
+// ws_out (TRAIN): bf16 operand rows of the workspace (or nullptr); ws_row = first feature row of this warp's 64,
+// ws_col = this thread's sample
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
-                                              unsigned short *ws_out = nullptr, int ws_ch = 0, unsigned long long *mask_out = nullptr)
+                                              unsigned short *ws_out = nullptr, int ws_row = 0, int ws_col = 0,
+                                              unsigned long long *mask_out = nullptr)
 {
     uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
@@ -453,8 +455,8 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
             unsigned long long bits = 0ull;      // + the ReLU mask of these 64 activations for the dgrad chain
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                ws_out[(size_t)(2 * i) * ws_ch] = (unsigned short)(pk[i] & 0xffffu);
-                ws_out[(size_t)(2 * i + 1) * ws_ch] = (unsigned short)(pk[i] >> 16);
+                ws_out[big_off(ws_row + 2 * i, ws_col)] = (unsigned short)(pk[i] & 0xffffu);
+                ws_out[big_off(ws_row + 2 * i + 1, ws_col)] = (unsigned short)(pk[i] >> 16);
                 bits |= (unsigned long long)((pk[i] & 0xffffu) != 0u) << (2 * i);
                 bits |= (unsigned long long)((pk[i] >> 16) != 0u) << (2 * i + 1);
             }
@@ -553,7 +555,7 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
             if (col >= 0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    reinterpret_cast<__nv_bfloat16 *>(ws)[(size_t)(R_C0H + 32 * g + 4 * i + j) * ws_ch + col] = __float2bfloat16_rn(v[j]);
+                    reinterpret_cast<__nv_bfloat16 *>(ws)[big_off(R_C0H + 32 * g + 4 * i + j, col)] = __float2bfloat16_rn(v[j]);
                     mbits[g] |= (unsigned int)(v[j] > 0.f) << (4 * i + j);
                 }
             }
@@ -741,16 +743,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
                     unsigned short *ws_out = nullptr;
                     unsigned long long *mask_out = nullptr;
+                    int col = -1;
                     if (TRAIN) {
-                        const int col = ws_col(a, row_info(a, tile_begin + t, row));
+                        col = ws_col(a, row_info(a, tile_begin + t, row));
                         if (col >= 0) {
-                            ws_out = reinterpret_cast<unsigned short *>(a.ws) + (size_t)(R_H + layer * 256 + hh * 128 + 64 * w2) * a.ws_ch + col;
+                            ws_out = reinterpret_cast<unsigned short *>(a.ws);
                             mask_out = reinterpret_cast<unsigned long long *>(a.ws + (size_t)R_MASK * a.ws_ch) +
                                        (size_t)(layer * 4 + hh * 2 + w2) * a.ws_ch + col;
                         }
                     }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, a.ws_ch, mask_out);
+                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, R_H + layer * 256 + hh * 128 + 64 * w2, col, mask_out);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();

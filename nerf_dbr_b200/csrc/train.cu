@@ -32,10 +32,10 @@ constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per S
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
                      float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream);
 int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, cudaStream_t stream);
-int wgrad_skinny(const float *A, int rows_a, const __nv_bfloat16 *B, int rows_b, int ch, float *dW, int ld, float *dbias,
+int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias,
                  cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
-int wgrad_tc(const __nv_bfloat16 *A, int rows_a, const __nv_bfloat16 *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
+int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream);
 
 struct TrainArgs {
@@ -420,9 +420,8 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
             // forward on the tensor cores (TRAIN variant of the fused kernel); pad columns of the stored
             // activations must be finite zeros: wgrad multiplies them by zero gradients
             const int n_smp = a.n_rays * n_samples;
-            if (a.ch != n_smp)                          // bf16 operand rows: pitch ch * 2 bytes
-                cudaMemset2DAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + n_smp, (size_t)a.ch * 2, 0, (size_t)(a.ch - n_smp) * 2,
-                                  R_DE + 32, stream);
+            if (a.ch != n_smp)                          // the last slab of the bf16 operand rows (activations and dpre)
+                cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)R_BIG * 128, stream);
             const float *tr = t_rand ? t_rand + (size_t)r0 * n_samples : nullptr;
             if ((rc = tc_train_forward(packed, rays_o + 3 * (size_t)r0, rays_d + 3 * (size_t)r0, a.n_rays, n_samples, near, far,
                                        tr, a.ws, a.ch, nullptr, stream)))
@@ -434,11 +433,9 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         train_ray_kernel<<<std::min((a.n_rays + 7) / 8, sms * 8), 256, 0, stream>>>(a);
         if ((rc = launch_status())) return rc;
         if (tc) {
-            // dgrad chain on the tensor cores; the pad columns of the dpre rows must be zero for wgrad
+            // dgrad chain on the tensor cores; the pad columns of the dpre rows are zero since the memset above
             const int n_smp = a.n_rays * n_samples;
             if (a.ch != n_smp) {
-                cudaMemset2DAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + (size_t)R_DPRE * a.ch + n_smp, (size_t)a.ch * 2, 0,
-                                  (size_t)(a.ch - n_smp) * 2, R_DPREC0 + 128 - R_DPRE, stream);
                 cudaMemset2DAsync(a.ws + (size_t)R_DSIG * a.ch + n_smp, (size_t)a.ch * sizeof(float), 0,
                                   (size_t)(a.ch - n_smp) * sizeof(float), 4, stream);       // dsig, dy (fp32 rows)
             }
@@ -455,12 +452,12 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
             if (tc) {
-                // BF16 mode: the big operand rows are bf16 at the same row numbers (train_layout.h)
+                // BF16 mode: the big operand rows are slab-major bf16 under the same row numbers (train_layout.h)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
-                const __nv_bfloat16 *Bb = wsb + (size_t)(B - ws);
+                const int row_a = (int)((A - ws) / ch), row_b = (int)((B - ws) / ch);
                 if (rows_a <= 4)
-                    return wgrad_skinny(A, rows_a, Bb, rows_b, (int)ch, const_cast<float *>(dW), ld, const_cast<float *>(db), stream);
-                return wgrad_tc(wsb + (size_t)(A - ws), rows_a, Bb, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
+                    return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db), stream);
+                return wgrad_tc(wsb, row_a, rows_a, row_b, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
                                 const_cast<float *>(db), scratch, kWgradSplits, stream);
             }
             dim3 grid((rows_a + 63) / 64, (rows_b + 63) / 64, split);

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     tmem_ld32(t_cols + 32, xb);
                     tmem_ld_wait();
                     const unsigned long long m = on ? mbits[hh] : 0ull;      // ReLU mask of these 64 activations
-                    unsigned short *dp = reinterpret_cast<unsigned short *>(a.ws) + (size_t)(R_DPRE + layer * 256 + n0) * ch + col;
+                    unsigned short *dp = reinterpret_cast<unsigned short *>(a.ws);
+                    const int r0 = R_DPRE + layer * 256 + n0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         // bf16 pairs: the values wgrad multiplies are exactly the ones the next GEMM of the chain sees
@@ -176,10 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         pk[i] = pack_bf16(a0, a1);
                         pk[16 + i] = pack_bf16(b0, b1);
                         if (on) {
-                            dp[(size_t)(2 * i) * ch] = (unsigned short)(pk[i] & 0xffffu);
-                            dp[(size_t)(2 * i + 1) * ch] = (unsigned short)(pk[i] >> 16);
-                            dp[(size_t)(32 + 2 * i) * ch] = (unsigned short)(pk[16 + i] & 0xffffu);
-                            dp[(size_t)(33 + 2 * i) * ch] = (unsigned short)(pk[16 + i] >> 16);
+                            dp[big_off(r0 + 2 * i, col)] = (unsigned short)(pk[i] & 0xffffu);
+                            dp[big_off(r0 + 2 * i + 1, col)] = (unsigned short)(pk[i] >> 16);
+                            dp[big_off(r0 + 32 + 2 * i, col)] = (unsigned short)(pk[16 + i] & 0xffffu);
+                            dp[big_off(r0 + 33 + 2 * i, col)] = (unsigned short)(pk[16 + i] >> 16);
                         }
                     }
                     if (g < kDgGemms - 1) {
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         for (int j = 0; j < 4; ++j) {
                             const int n = 64 * kb + 4 * i + j;
                             if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
-                            reinterpret_cast<__nv_bfloat16 *>(a.ws)[(size_t)(R_DPREC0 + n) * ch + col] = __float2bfloat16_rn(v[j]);
+                            reinterpret_cast<__nv_bfloat16 *>(a.ws)[big_off(R_DPREC0 + n, col)] = __float2bfloat16_rn(v[j]);
                         }
                     }
                     pk[2 * i] = pack_bf16(v[0], v[1]);

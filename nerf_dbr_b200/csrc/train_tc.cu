@@ -2,40 +2,44 @@
 //
 // wgrad_tc_kernel -- dW[n][k] = sum_s dY[n][s] X[k][s] for one parameter tensor, as a tcgen05 GEMM with
 // M = n (128 or 256 output features), N = k (up to 256 input features), K = samples.  Both operands sit in
-// the training workspace K-major ([feature][sample], bf16 -- exactly the values the forward and the dgrad chain
-// multiplied); loader warps copy 64-sample slabs straight into the 128B-swizzled K-major shared-memory tiles the MMA reads (A: [rows_a x 64],
-// B: [rows_b x 64], two stages); the fp32 accumulators of the whole 256 x 256 tensor fill the 512 TMEM
-// columns.  The sample range is split over CTAs; each writes its partial to scratch and
-// wgrad_reduce_kernel folds the partials into the caller's gradient tensor (no atomics).
+// the training workspace as bf16 -- exactly the values the forward and the dgrad chain multiplied -- slab-major and
+// pre-swizzled (train_layout.h: big_off), so the operand tile of a 64-sample slab is one contiguous block that is
+// already the 128B-swizzled K-major shared-memory image: one thread stages it with two cp.async.bulk copies
+// (A: [rows_a x 64], B: [rows_b x 64], three stages in flight -- the kernel is HBM-bound).  The fp32 accumulators of
+// the whole 256 x 256 tensor fill the 512 TMEM columns.  The slab range is split over CTAs; each writes its partial
+// to scratch and wgrad_reduce_kernel folds the partials into the caller's gradient tensor.  Bias gradients (row
+// sums of A) are taken from the staged tiles in shared memory by the otherwise idle epilogue warps.
 //
 // reference: the autograd backward of the ten nn.Linear layers in NeRFModel (src/models/nerf.py:72-90)
 // inside NeRFTrainer.train_step (src/training/trainer.py:125-126).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "train_layout.h"
+#include <algorithm>
 
 namespace nerfb200 {
 namespace wg {
 
 using namespace ptx;
 
-constexpr int kThreads = 512;
-constexpr int kLoaderWarps = 12;                 // warps 4..15
+constexpr int kThreads = 384;                    // warp 0 producer, 1 MMA issuer, 2 TMEM owner, 4..11 bias sums + epilogue
+constexpr int kStages = 3;
 constexpr uint32_t kTileA = 256 * 128;           // [256 x 64] bf16
 constexpr uint32_t kTileB = 256 * 128;
 constexpr uint32_t kStage = kTileA + kTileB;     // 64 KB
-constexpr uint32_t SM_BAR = 2 * kStage;
+constexpr uint32_t SM_BAR = kStages * kStage;
 constexpr uint32_t SM_TMEM = SM_BAR + 64;
 constexpr uint32_t kSmem = SM_TMEM + 16 + 1024;
 
-enum { B_FULL = 0, B_EMPTY = 2, B_DONE = 4 };
+enum { B_FULL = 0, B_EMPTY = kStages, B_DONE = 2 * kStages };
 
 struct Args {
-    const __nv_bfloat16 *A; int rows_a;          // 128 or 256
-    const __nv_bfloat16 *B; int rows_b;                  // padded to a multiple of 16, <= 256; rows >= rows_b_valid read as 0
-    int rows_b_valid;
-    int ch;                                      // samples (multiple of 64)
+    const __nv_bfloat16 *ws;                     // bf16 operand rows (slab-major)
+    int row_a, rows_a;                           // A = rows [row_a, row_a + rows_a), rows_a = 128 or 256
+    int row_b, rows_b;                           // B rows, padded to a multiple of 16, <= 256 (pad rows hold zeros)
+    int n_slabs;                                 // samples / 64
     float *partial;                              // [gridDim.x][rows_a][rows_b]
-    float *dbias;                                // optional: dbias[n] += sum_s A[n][s] (fp32, from the loader's registers)
+    float *dbias;                                // optional: dbias[n] += sum_s A[n][s]
 };
 
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
@@ -52,13 +56,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
     const uint32_t sm_base = smem_u32(sm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) { return sm_base + SM_BAR + 8u * i; };
-    const int n_chunks = a.ch / 64;
-    const int per = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const int c_begin = blockIdx.x * per, c_end = min(n_chunks, c_begin + per);
-    const int my_chunks = max(0, c_end - c_begin);
+    const int per = (a.n_slabs + gridDim.x - 1) / gridDim.x;
+    const int c_begin = blockIdx.x * per, c_end = min(a.n_slabs, c_begin + per);
+    const int my_slabs = max(0, c_end - c_begin);
+    const bool want_bias = a.dbias != nullptr;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_FULL + i), kLoaderWarps); mbar_init(bar(B_EMPTY + i), 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar(B_FULL + i), 1); mbar_init(bar(B_EMPTY + i), want_bias ? 9 : 1); }
         mbar_init(bar(B_DONE), 1);
         fence_mbar_init();
     }
@@ -69,12 +73,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_TMEM);
     const int m_blocks = a.rows_a / 128;
 
-    if (warp == 1) {
+    if (warp == 0) {
+        // ---------------- producer: two bulk copies per slab
+        if (lane == 0) {
+            const uint32_t bytes_a = (uint32_t)a.rows_a * 128u, bytes_b = (uint32_t)a.rows_b * 128u;
+            for (int c = 0; c < my_slabs; ++c) {
+                const int s = c % kStages, use = c / kStages;
+                if (use > 0) wait(bar(B_EMPTY + s), (use - 1) & 1);
+                mbar_arrive_expect_tx(bar(B_FULL + s), bytes_a + bytes_b);
+                bulk_g2s(sm_base + s * kStage, a.ws + big_tile(a.row_a, c_begin + c), bytes_a, bar(B_FULL + s));
+                bulk_g2s(sm_base + s * kStage + kTileA, a.ws + big_tile(a.row_b, c_begin + c), bytes_b, bar(B_FULL + s));
+            }
+        }
+    } else if (warp == 1) {
         // ---------------- MMA issuer
         const uint32_t idesc = idesc_bf16(128, (uint32_t)a.rows_b);
-        for (int c = 0; c < my_chunks; ++c) {
-            const int s = c & 1;
-            wait(bar(B_FULL + s), (c >> 1) & 1);
+        for (int c = 0; c < my_slabs; ++c) {
+            const int s = c % kStages, use = c / kStages;
+            wait(bar(B_FULL + s), use & 1);
             tc_fence_after_sync();
             if (elect_one()) {
                 const uint64_t adesc = smem_desc_sw128(sm_base + s * kStage);
@@ -85,78 +101,47 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                         mma_bf16_ss(tmem_base + mb * 256, adesc + (uint64_t)((mb * 16384) >> 4) + 2 * k, bdesc + 2 * k, idesc,
                                     (c | k) != 0);
                 mma_commit(bar(B_EMPTY + s));
-                if (c == my_chunks - 1) mma_commit(bar(B_DONE));
+                if (c == my_slabs - 1) mma_commit(bar(B_DONE));
             }
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ---------------- loaders: fp32 [row][sample] -> bf16 swizzled K-major tiles
-        const int lt = (warp - 4) * 32 + lane, n_lt = kLoaderWarps * 32;
-        const int units_a = a.rows_a * 8, units_b = a.rows_b * 8;      // 16-byte units (8 samples) per 64-sample slab
-        // a thread meets the same A rows in every slab (unit index -> row is slab-independent): bias partial sums
-        // ride in registers, one per batch slot
-        float bsum[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        for (int c = 0; c < my_chunks; ++c) {
-            const int s = c & 1;
-            if (c >= 2) wait(bar(B_EMPTY + s), ((c >> 1) - 1) & 1);
-            const size_t s0 = (size_t)(c_begin + c) * 64;
-            uint8_t *ta = sm + s * kStage, *tb = ta + kTileA;
-            // batches of 4 units per thread: 8 independent 16-byte loads in flight before the first conversion
-            // (the kernel is HBM-bound; a load-convert-store loop leaves the memory system idle)
-            int batch = 0;
-            for (int u0 = lt; u0 < units_a + units_b; u0 += 4 * n_lt, ++batch) {
-                uint4 x[4];
+        const int ew = warp - 4;                       // 8 warps
+        // ---------------- bias gradients: thread t sums row t of every staged A tile (all eight 16-byte units of
+        // the row, so the swizzle does not matter; lanes start at rotated units to spread the banks)
+        if (want_bias) {
+            const int t = ew * 32 + lane;
+            float bs = 0.f;
+            for (int c = 0; c < my_slabs; ++c) {
+                const int s = c % kStages, use = c / kStages;
+                wait(bar(B_FULL + s), use & 1);
+                if (t < a.rows_a) {
+                    const uint32_t rowp = sm_base + s * kStage + t * 128;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int u = u0 + b * n_lt;
-                    const bool is_a = u < units_a;
-                    const int v = is_a ? u : u - units_a;
-                    const int row = v >> 3, cu = v & 7;
-                    x[b] = make_uint4(0u, 0u, 0u, 0u);
-                    if (u < units_a + units_b && (is_a || row < a.rows_b_valid))
-                        x[b] = __ldg(reinterpret_cast<const uint4 *>((is_a ? a.A : a.B) + (size_t)row * a.ch + s0 + cu * 8));
-                }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = ld_shared_f4(rowp + (((j + lane) & 7) << 4));
+                        const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int u = u0 + b * n_lt;
-                    if (u >= units_a + units_b) continue;
-                    const bool is_a = u < units_a;
-                    const int v = is_a ? u : u - units_a;
-                    const int row = v >> 3, cu = v & 7;
-                    *reinterpret_cast<uint4 *>((is_a ? ta : tb) + row * 128 + ((cu ^ (row & 7)) << 4)) = x[b];
-                    if (is_a && batch < 2) {
-                        const uint32_t w[4] = {x[b].x, x[b].y, x[b].z, x[b].w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) bsum[batch][b] += __uint_as_float(w[j] << 16) + __uint_as_float(w[j] & 0xffff0000u);
+                        for (int i = 0; i < 4; ++i) bs += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_EMPTY + s));
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_FULL + s));
-        }
-        if (a.dbias) {                                  // units_a <= 2048 = 2 batches of 4 x 384 threads (less 1024)
-#pragma unroll
-            for (int batch = 0; batch < 2; ++batch)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int u = lt + (batch * 4 + b) * n_lt;
-                    if (u < units_a && bsum[batch][b] != 0.f) atomicAdd(a.dbias + (u >> 3), bsum[batch][b]);
-                }
+            if (t < a.rows_a && bs != 0.f) atomicAdd(a.dbias + t, bs);
         }
         // ---------------- epilogue: accumulators -> this CTA's partial
-        if (my_chunks > 0) {
+        if (my_slabs > 0) {
             wait(bar(B_DONE), 0);
             tc_fence_after_sync();
         }
-        const int ew = warp - 4;                       // 12 warps; warps 0..7 cover (m block, lane quadrant)
         if (ew < 4 * m_blocks) {
             const int mb = ew >> 2, q = warp & 3;      // TMEM lane quadrant = warp % 4
             const int n = mb * 128 + q * 32 + lane;
             float *dst = a.partial + ((size_t)blockIdx.x * a.rows_a + n) * a.rows_b;
             for (int col = 0; col < a.rows_b; col += 32) {
                 uint32_t v[32];
-                if (my_chunks > 0) {
+                if (my_slabs > 0) {
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 256 + col, v);
                     tmem_ld_wait();
                 } else {
@@ -188,89 +173,84 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int split
     }
 }
 
-// dbias[n] += sum_s A[n][s]; one block per row (a row is up to 1 MB: the whole GPU has to pull)
-__global__ void __launch_bounds__(256) rowsum_kernel(const float *__restrict__ A, int rows, int ch, float *__restrict__ dbias)
-{
-    __shared__ float part[8];
-    const int r = blockIdx.x;
-    if (r >= rows) return;
-    const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)r * ch);
-    float s = 0.f;
-    for (int i = threadIdx.x; i < ch / 4; i += 256) { float4 v = __ldg(p + i); s += (v.x + v.y) + (v.z + v.w); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += part[i];
-        dbias[r] += t;
-    }
-}
-
 // Skinny weight gradients (density head: 1 output row; colour layer 1: 3): dW[a][k] += sum_s A[a][s] B[k][s],
-// dbias[a] += sum_s A[a][s].  One block per input feature k streams B's row once; A (<= 4 rows) stays in L2.
-__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, const __nv_bfloat16 *__restrict__ B,
-                                                           int rows_b, int ch, float *__restrict__ dW, int ld,
-                                                           float *__restrict__ dbias)
+// dbias[a] += sum_s A[a][s].  A is fp32 [row][ch]; B is a slab-major bf16 operand group.  A block walks slabs:
+// it stages the slab's contiguous B tile (coalesced 16-byte loads) and the 64 A values per row in shared memory,
+// thread k takes the dot products of B row k, and the block's totals go out as one atomicAdd per element.
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, int ch,
+                                                           const __nv_bfloat16 *__restrict__ ws, int row_b, int rows_b,
+                                                           float *__restrict__ dW, int ld, float *__restrict__ dbias)
 {
-    __shared__ float part[8][5];
-    const int k = blockIdx.x;                      // k == rows_b: the bias block (B row of ones)
-    const uint2 *bp = k < rows_b ? reinterpret_cast<const uint2 *>(B + (size_t)k * ch) : nullptr;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = threadIdx.x; i < ch / 4; i += 256) {
-        float4 b = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (bp) {
-            const uint2 r = __ldg(bp + i);
-            b = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
-                            __uint_as_float(r.y & 0xffff0000u));
+    __shared__ __align__(16) uint4 tile[256 * 8];          // [rows_b][8 units], swizzled as stored
+    __shared__ __align__(16) float as[4][64];
+    const int k = threadIdx.x, n_slabs = ch / 64;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bs = 0.f;
+    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ws + big_tile(row_b, slab));
+        for (int i = threadIdx.x; i < rows_b * 8; i += 256) tile[i] = __ldg(src + i);
+        if (threadIdx.x < 16 * rows_a) {
+            const int r = threadIdx.x >> 4, j = threadIdx.x & 15;
+            reinterpret_cast<float4 *>(as[r])[j] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)r * ch + (size_t)slab * 64) + j);
         }
+        __syncthreads();
+        if (k < rows_b) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = (j + k) & 7;                 // rotated start: conflict-free 16-byte reads
+                const uint4 v = tile[k * 8 + p];
+                const int g = p ^ (k & 7);                 // sample group held by unit p of row k
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (r < rows_a) {
+                        const float4 a0 = reinterpret_cast<const float4 *>(as[r])[2 * g], a1 = reinterpret_cast<const float4 *>(as[r])[2 * g + 1];
+                        acc[r] += (a0.x * __uint_as_float(w[0] << 16) + a0.y * __uint_as_float(w[0] & 0xffff0000u)) +
+                                  (a0.z * __uint_as_float(w[1] << 16) + a0.w * __uint_as_float(w[1] & 0xffff0000u)) +
+                                  (a1.x * __uint_as_float(w[2] << 16) + a1.y * __uint_as_float(w[2] & 0xffff0000u)) +
+                                  (a1.z * __uint_as_float(w[3] << 16) + a1.w * __uint_as_float(w[3] & 0xffff0000u));
+                    }
+            }
+        }
+        if (dbias && threadIdx.x >= 224 && threadIdx.x - 224 < rows_a) {   // bias: the last warp's first lanes
+            const float *ar = as[threadIdx.x - 224];
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) bs += ar[j];
+        }
+        __syncthreads();
+    }
+    if (k < rows_b)
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            if (r < rows_a) {
-                const float4 av = __ldg(reinterpret_cast<const float4 *>(A + (size_t)r * ch) + i);
-                s[r] += (av.x * b.x + av.y * b.y) + (av.z * b.z + av.w * b.w);
-            }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
-    if ((threadIdx.x & 31) == 0)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) part[threadIdx.x >> 5][r] = s[r];
-    __syncthreads();
-    if (threadIdx.x < rows_a) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
-        if (k < rows_b) dW[(size_t)threadIdx.x * ld + k] += t;
-        else if (dbias) dbias[threadIdx.x] += t;
-    }
+            if (r < rows_a && acc[r] != 0.f) atomicAdd(dW + (size_t)r * ld + k, acc[r]);
+    if (dbias && threadIdx.x >= 224 && threadIdx.x - 224 < rows_a && bs != 0.f) atomicAdd(dbias + (threadIdx.x - 224), bs);
 }
 
 }  // namespace wg
 
-int wgrad_skinny(const float *A, int rows_a, const __nv_bfloat16 *B, int rows_b, int ch, float *dW, int ld, float *dbias,
-                 cudaStream_t stream)
+int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld,
+                 float *dbias, cudaStream_t stream)
 {
-    wg::wgrad_skinny_kernel<<<rows_b + 1, 256, 0, stream>>>(A, rows_a, B, rows_b, ch, dW, ld, dbias);
+    if (rows_a > 4 || rows_b > 256) return NERF_B200_EINVAL;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(ch / 64, 4 * sms);
+    wg::wgrad_skinny_kernel<<<grid, 256, 0, stream>>>(A, rows_a, ch, ws, row_b, rows_b, dW, ld, dbias);
     return launch_status();
 }
 
 size_t wgrad_tc_scratch_bytes(int splits) { return (size_t)splits * 256 * 256 * sizeof(float); }
 
-// dW (+)= A^T-by-B over the chunk's samples on the tensor cores; bias row sums on CUDA cores.
-int wgrad_tc(const __nv_bfloat16 *A, int rows_a, const __nv_bfloat16 *B, int rows_b_valid, int ch, float *dW, int ld, int col_off,
+// dW (+)= A-by-B^T over the chunk's samples on the tensor cores; A and B are row groups of the slab-major bf16
+// operand rows at `ws`.
+int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream)
 {
     wg::Args a = {};
-    a.A = A; a.rows_a = rows_a; a.B = B; a.rows_b_valid = rows_b_valid;
+    a.ws = ws; a.row_a = row_a; a.rows_a = rows_a; a.row_b = row_b;
     a.rows_b = (rows_b_valid + 15) / 16 * 16;
-    a.ch = ch; a.partial = scratch; a.dbias = dbias;
-    const int n_chunks = ch / 64;
-    if (splits > n_chunks) splits = n_chunks;
+    a.n_slabs = ch / 64; a.partial = scratch; a.dbias = dbias;
+    if (splits > a.n_slabs) splits = a.n_slabs;
     cudaError_t e = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     wg::wgrad_tc_kernel<<<splits, wg::kThreads, wg::kSmem, stream>>>(a);
@@ -278,8 +258,7 @@ int wgrad_tc(const __nv_bfloat16 *A, int rows_a, const __nv_bfloat16 *B, int row
     if (rc) return rc;
     const int total = rows_a * rows_b_valid;
     wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.rows_b, rows_b_valid, dW, ld, col_off);
-    if ((rc = launch_status())) return rc;
-    return rc;
+    return launch_status();
 }
 
 }  // namespace nerfb200
