@@ -235,9 +235,10 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
     if (TRAIN) {                                           // the bf16 values the MMA sees, [feature][sample] for wgrad
         const int col = ws_col(a, ri);
         if (col >= 0) {
-            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws);
+            uint32_t pk[32];
 #pragma unroll
-            for (int f = 0; f < 64; ++f) p[big_off(R_PE + f, col)] = __float2bfloat16_rn(feat[f]);
+            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16(feat[2 * i], feat[2 * i + 1]);
+            store_block_row(a.ws, G_PE, col, pk);
         }
     }
     const uint32_t pe_row = smem_u32(sm + SM_PE + pe_buf * 16384 + row * 128);
@@ -288,9 +289,11 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
         const int col = ws_col(a, ri);
         if (col >= 0) {
             const int q = a.tiles_per_ray == 1 ? (row >> a.s_pad_log2) : 0;
-            __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.ws);
+            uint32_t pk[32];
 #pragma unroll
-            for (int f = 0; f < 32; ++f) p[big_off(R_DE + f, col)] = __float2bfloat16_rn(f < kDirFeat ? de[q * 32 + f] : 0.f);
+            for (int i = 0; i < 32; ++i)
+                pk[i] = i < 16 ? pack_bf16(2 * i < kDirFeat ? de[q * 32 + 2 * i] : 0.f, 2 * i + 1 < kDirFeat ? de[q * 32 + 2 * i + 1] : 0.f) : 0u;
+            store_block_row(a.ws, G_DE, col, pk);
         }
     }
     named_bar_sync(1, 128);          // de[] is rewritten by the next produce
@@ -451,16 +454,21 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
         bias_relu_pack(xa, pk, bias_addr);
         bias_relu_pack(xb, pk + 16, bias_addr + 128);
         tmem_st32(t_cols, pk);                   // K-block: 64 bf16 in columns [0, 32) of this warp's range
-        if (ws_out) {                            // exactly what the next layer multiplies: the bf16-rounded values
+        if (ws_out) {                            // TRAIN: hand the operand to the next layer first, then store
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready);
+            // exactly what the next layer multiplies: the bf16-rounded values (128 contiguous bytes per sample)
+            store_block_row(ws_out, ws_row, ws_col, pk);
             unsigned long long bits = 0ull;      // + the ReLU mask of these 64 activations for the dgrad chain
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                ws_out[big_off(ws_row + 2 * i, ws_col)] = (unsigned short)(pk[i] & 0xffffu);
-                ws_out[big_off(ws_row + 2 * i + 1, ws_col)] = (unsigned short)(pk[i] >> 16);
                 bits |= (unsigned long long)((pk[i] & 0xffffu) != 0u) << (2 * i);
                 bits |= (unsigned long long)((pk[i] >> 16) != 0u) << (2 * i + 1);
             }
             *mask_out = bits;
+            return;
         }
     } else {
         uint32_t hi[16], lo[16];                 // hi halves in columns [0, 32), lo halves in [32, 64)
@@ -533,7 +541,7 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
     unsigned int mbits[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
-        uint32_t x[32];
+        uint32_t x[32], pk[16];
         tmem_ld32(t_row + 32 * g, x);
         tmem_ld_wait();
         if (g == 3) {                                       // the accumulator is in registers
@@ -552,13 +560,16 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
             r[0] = fmaf(v[0], w0.x, r[0]); r[0] = fmaf(v[1], w0.y, r[0]); r[0] = fmaf(v[2], w0.z, r[0]); r[0] = fmaf(v[3], w0.w, r[0]);
             r[1] = fmaf(v[0], w1.x, r[1]); r[1] = fmaf(v[1], w1.y, r[1]); r[1] = fmaf(v[2], w1.z, r[1]); r[1] = fmaf(v[3], w1.w, r[1]);
             r[2] = fmaf(v[0], w2.x, r[2]); r[2] = fmaf(v[1], w2.y, r[2]); r[2] = fmaf(v[2], w2.z, r[2]); r[2] = fmaf(v[3], w2.w, r[2]);
-            if (col >= 0) {
+            pk[2 * i] = pack_bf16(v[0], v[1]);
+            pk[2 * i + 1] = pack_bf16(v[2], v[3]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    reinterpret_cast<__nv_bfloat16 *>(ws)[big_off(R_C0H + 32 * g + 4 * i + j, col)] = __float2bfloat16_rn(v[j]);
-                    mbits[g] |= (unsigned int)(v[j] > 0.f) << (4 * i + j);
-                }
-            }
+            for (int j = 0; j < 4; ++j) mbits[g] |= (unsigned int)(v[j] > 0.f) << (4 * i + j);
+        }
+        if (col >= 0) {                                     // 32 features = four 16-byte units of this sample's row
+            uint4 *rowp = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(ws) + big_row(G_C0H + 64 * (g >> 1), col));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                rowp[((g & 1) * 4 + u) ^ (col & 7)] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         }
     }
     if (col >= 0) {
@@ -753,7 +764,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                         }
                     }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, R_H + layer * 256 + hh * 128 + 64 * w2, col, mask_out);
+                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, G_H + layer * 256 + hh * 128 + 64 * w2, col, mask_out);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();

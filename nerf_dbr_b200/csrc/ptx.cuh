@@ -146,6 +146,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// Same for an MN-major operand (the K index is the slow one): a tile is [block of 64 MN][k][64 MN elements] bf16 --
+// 128-byte rows indexed by k, 16-byte units XOR-swizzled by (k & 7); stride byte offset = 1024 between groups of
+// 8 k, leading byte offset = bytes between blocks of 64 MN elements.  One K = 16 step advances the start by 2048 B.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t block_bytes)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(block_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // Instruction descriptor, .kind::f16, A = B = bf16, D = fp32, both operands K-major:
 //   [4,6) D format: 1 = f32   [7,10) A format: 1 = bf16   [10,13) B format: 1 = bf16
 //   [15] A major: 0 = K       [16] B major: 0 = K         [17,23) N >> 3   [24,29) M >> 4
@@ -153,6 +161,8 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n)
 {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// ... both operands MN-major
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(uint32_t m, uint32_t n) { return idesc_bf16(m, n) | (1u << 15) | (1u << 16); }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
 {

@@ -421,7 +421,7 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
             // activations must be finite zeros: wgrad multiplies them by zero gradients
             const int n_smp = a.n_rays * n_samples;
             if (a.ch != n_smp)                          // the last slab of the bf16 operand rows (activations and dpre)
-                cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)R_BIG * 128, stream);
+                cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)G_TOTAL * 128, stream);
             const float *tr = t_rand ? t_rand + (size_t)r0 * n_samples : nullptr;
             if ((rc = tc_train_forward(packed, rays_o + 3 * (size_t)r0, rays_d + 3 * (size_t)r0, a.n_rays, n_samples, near, far,
                                        tr, a.ws, a.ch, nullptr, stream)))
@@ -452,9 +452,9 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
             if (tc) {
-                // BF16 mode: the big operand rows are slab-major bf16 under the same row numbers (train_layout.h)
+                // BF16 mode: the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
-                const int row_a = (int)((A - ws) / ch), row_b = (int)((B - ws) / ch);
+                const int row_a = big_feature((int)((A - ws) / ch)), row_b = big_feature((int)((B - ws) / ch));
                 if (rows_a <= 4)
                     return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db), stream);
                 return wgrad_tc(wsb, row_a, rows_a, row_b, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,

@@ -165,8 +165,6 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     tmem_ld32(t_cols + 32, xb);
                     tmem_ld_wait();
                     const unsigned long long m = on ? mbits[hh] : 0ull;      // ReLU mask of these 64 activations
-                    unsigned short *dp = reinterpret_cast<unsigned short *>(a.ws);
-                    const int r0 = R_DPRE + layer * 256 + n0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         // bf16 pairs: the values wgrad multiplies are exactly the ones the next GEMM of the chain sees
@@ -176,20 +174,15 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         const float b1 = (m >> (33 + 2 * i)) & 1ull ? __uint_as_float(xb[2 * i + 1]) : 0.f;
                         pk[i] = pack_bf16(a0, a1);
                         pk[16 + i] = pack_bf16(b0, b1);
-                        if (on) {
-                            dp[big_off(r0 + 2 * i, col)] = (unsigned short)(pk[i] & 0xffffu);
-                            dp[big_off(r0 + 2 * i + 1, col)] = (unsigned short)(pk[i] >> 16);
-                            dp[big_off(r0 + 32 + 2 * i, col)] = (unsigned short)(pk[16 + i] & 0xffffu);
-                            dp[big_off(r0 + 33 + 2 * i, col)] = (unsigned short)(pk[16 + i] >> 16);
-                        }
                     }
-                    if (g < kDgGemms - 1) {
+                    if (g < kDgGemms - 1) {                                // hand the operand to the next GEMM first
                         tmem_st32(t_cols, pk);
                         tmem_st_wait();
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
                     }
+                    if (on) store_block_row(a.ws, G_DPRE + layer * 256 + n0, col, pk);   // 128 contiguous bytes per sample
                 }
             }
             // region 1 (G7's accumulator) has been read: the next tile's G0 operand may be written there
@@ -226,17 +219,13 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     const float4 w2 = ld_shared_f4(wc1 + 1024 + (64 * kb + 4 * i) * 4);
                     float v[4] = {dy[0] * w0.x + dy[1] * w1.x + dy[2] * w2.x, dy[0] * w0.y + dy[1] * w1.y + dy[2] * w2.y,
                                   dy[0] * w0.z + dy[1] * w1.z + dy[2] * w2.z, dy[0] * w0.w + dy[1] * w1.w + dy[2] * w2.w};
-                    if (on) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int n = 64 * kb + 4 * i + j;
-                            if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
-                            reinterpret_cast<__nv_bfloat16 *>(a.ws)[big_off(R_DPREC0 + n, col)] = __float2bfloat16_rn(v[j]);
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
                     pk[2 * i] = pack_bf16(v[0], v[1]);
                     pk[2 * i + 1] = pack_bf16(v[2], v[3]);
                 }
+                if (on) store_block_row(a.ws, G_DPREC0 + 64 * kb, col, pk);
                 tmem_st32(t_row + 64 * kb, pk);
             }
             {

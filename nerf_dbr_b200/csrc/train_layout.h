@@ -1,8 +1,8 @@
 // Training workspace layout shared by train.cu (FP32 kernels), train_tc.cu and the TRAIN variant of the fused
 // tensor-core kernel (mlp_tc.cu): [row][ch] fp32, K-major for the weight-gradient GEMMs (sample contiguous).
 #pragma once
-// BF16 mode keeps the big operand rows (R_PE, R_H, R_C0H, R_DE, R_DPRE, R_DPREC0) as bf16 in the first 8912 ch bytes of
-// the same buffer (slab-major, see big_off below; the first fp32 row it still uses, R_SIGPRE, starts at byte 9088 ch);
+// BF16 mode keeps the big operand rows (R_PE, R_H, R_C0H, R_DE, R_DPRE, R_DPREC0) as bf16 in the first 8960 ch bytes of
+// the same buffer (slab-major blocks, see G_* below; the first fp32 row it still uses, R_SIGPRE, starts at byte 9088 ch);
 // the small per-sample rows and the masks stay fp32 / uint64 [row][ch].
 namespace nerfb200 {
 constexpr int R_PE = 0;                      // 64   encoded position (row 63 = 0)
@@ -21,19 +21,48 @@ constexpr int R_MASK = R_DPREC0 + 128;       // 8 layers x 4 parts x 2 floats (o
 constexpr int R_MASKC0 = R_MASK + 64;        // colour layer 0: 2 parts x 2 floats
 constexpr int R_TOTAL = R_MASKC0 + 4;
 
-// BF16 mode: slab-major, pre-swizzled operand rows.  Samples are cut into slabs of 64; a slab holds every big row as
-// 128 bytes (64 bf16) in row order, and the eight 16-byte units of a row are XOR-swizzled by (row & 7) -- byte for byte
-// the 128B-swizzled K-major shared-memory image of a wgrad operand tile.  Rows [r0, r0 + n) of one slab are therefore
-// one contiguous n x 128 B block: wgrad stages an operand tile with a single cp.async.bulk, and the forward / dgrad
-// epilogues' stores land in a compact region instead of 64 pages.  (Every operand group starts at a multiple of 8
-// rows, so the swizzle by the global row number equals the swizzle by the row inside the tile.)
-constexpr int R_BIG = R_DPREC0 + 128;        // rows that exist as bf16 operand rows (R_PE .. R_DPREC0)
-static_assert(R_H % 8 == 0 && R_C0H % 8 == 0 && R_DE % 8 == 0 && R_DPRE % 8 == 0 && R_DPREC0 % 8 == 0, "tile-local swizzle");
-// element (bf16) offset of (row r, sample col)
-__host__ __device__ constexpr size_t big_off(int r, int col)
+// BF16 mode: slab-major, sample-major, pre-swizzled operand blocks.  The big operand rows are grouped in blocks of 64
+// features (G_* below, in features; every group starts on a block boundary) and the samples in slabs of 64.  One
+// (slab, block) is an 8 KB tile [64 samples][64 features] of bf16: a sample's 64 features are 128 contiguous bytes
+// whose eight 16-byte units are XOR-swizzled by (sample & 7).  That is byte for byte the 128B-swizzled *MN-major*
+// shared-memory image tcgen05 takes for a GEMM whose K dimension is the sample axis, so
+//   * a forward / dgrad epilogue thread (one sample, 64 features in registers) stores its 128 bytes with eight
+//     16-byte stores and a warp covers 4 KB contiguously (the [feature][sample] alternative costs 64 two-byte
+//     stores per thread), and
+//   * the operand tile of any row group for one slab is contiguous (blocks x 8 KB): wgrad stages it with a single
+//     cp.async.bulk and multiplies it in place (descriptor: LBO = 8 KB between feature blocks, SBO = 1 KB between
+//     groups of 8 samples).
+constexpr int G_PE = 0;                      // 64   encoded position (feature 63 = 0)
+constexpr int G_H = 64;                      // 8 x 256
+constexpr int G_C0H = G_H + 8 * 256;         // 128
+constexpr int G_DE = G_C0H + 128;            // 64   encoded direction (27 used, 32 written)
+constexpr int G_DPRE = G_DE + 64;            // 8 x 256
+constexpr int G_DPREC0 = G_DPRE + 8 * 256;   // 128
+constexpr int G_TOTAL = G_DPREC0 + 128;      // 4480 features = 70 blocks
+constexpr int kBlocksPerSlab = G_TOTAL / 64;
+static_assert((size_t)G_TOTAL * 2 <= (size_t)R_SIGPRE * 4, "bf16 operand blocks must end below the first fp32 row BF16 mode uses");
+// element (bf16) offset of the 128-byte row of sample `col` in the block that starts at feature g0 (multiple of 64)
+__host__ __device__ constexpr size_t big_row(int g0, int col)
 {
-    return ((size_t)(col >> 6) * R_BIG + r) * 64 + (size_t)(((((col & 63) >> 3) ^ (r & 7)) << 3) | (col & 7));
+    return (((size_t)(col >> 6) * kBlocksPerSlab + (g0 >> 6)) * 64 + (col & 63)) * 64;
 }
-// element offset of the tile rows [r0, ..) of slab `slab`
-__host__ __device__ constexpr size_t big_tile(int r0, int slab) { return ((size_t)slab * R_BIG + r0) * 64; }
+// element offset of the contiguous tile holding the blocks from feature g0 on, for slab `slab`
+__host__ __device__ constexpr size_t big_tile(int g0, int slab) { return ((size_t)slab * kBlocksPerSlab + (g0 >> 6)) * 4096; }
+// map a fp32-layout row number (R_*) of a big operand group to its feature number (G_*)
+__host__ __device__ constexpr int big_feature(int r)
+{
+    return r < R_SIGPRE ? (r < R_DE ? r : G_DE + (r - R_DE)) : G_DPRE + (r - R_DPRE);
+}
+
+#ifdef __CUDACC__
+// one sample's 64 features of one block: eight 16-byte stores (pk[4u .. 4u+3] = features 8u .. 8u+7 as bf16 pairs)
+__device__ __forceinline__ void store_block_row(void *ws, int g0, int col, const uint32_t (&pk)[32], int units = 8)
+{
+    uint4 *row = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(ws) + big_row(g0, col));
+    const int sw = col & 7;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (u < units) row[u ^ sw] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+}
+#endif
 }  // namespace nerfb200

@@ -2,10 +2,11 @@
 //
 // wgrad_tc_kernel -- dW[n][k] = sum_s dY[n][s] X[k][s] for one parameter tensor, as a tcgen05 GEMM with
 // M = n (128 or 256 output features), N = k (up to 256 input features), K = samples.  Both operands sit in
-// the training workspace as bf16 -- exactly the values the forward and the dgrad chain multiplied -- slab-major and
-// pre-swizzled (train_layout.h: big_off), so the operand tile of a 64-sample slab is one contiguous block that is
-// already the 128B-swizzled K-major shared-memory image: one thread stages it with two cp.async.bulk copies
-// (A: [rows_a x 64], B: [rows_b x 64], three stages in flight -- the kernel is HBM-bound).  The fp32 accumulators of
+// the training workspace as bf16 -- exactly the values the forward and the dgrad chain multiplied -- in slab-major,
+// sample-major, pre-swizzled blocks (train_layout.h), so the operand tile of a 64-sample slab is one contiguous
+// run of 8 KB blocks that is already the 128B-swizzled MN-major shared-memory image: one thread stages it with
+// two cp.async.bulk copies (A: rows_a/64 blocks, B: rows_b/64 blocks, three stages in flight -- the kernel is
+// HBM-bound) and the MMAs take both operands MN-major.  The fp32 accumulators of
 // the whole 256 x 256 tensor fill the 512 TMEM columns.  The slab range is split over CTAs; each writes its partial
 // to scratch and wgrad_reduce_kernel folds the partials into the caller's gradient tensor.  Bias gradients (row
 // sums of A) are taken from the staged tiles in shared memory by the otherwise idle epilogue warps.
@@ -35,8 +36,9 @@ enum { B_FULL = 0, B_EMPTY = kStages, B_DONE = 2 * kStages };
 
 struct Args {
     const __nv_bfloat16 *ws;                     // bf16 operand rows (slab-major)
-    int row_a, rows_a;                           // A = rows [row_a, row_a + rows_a), rows_a = 128 or 256
-    int row_b, rows_b;                           // B rows, padded to a multiple of 16, <= 256 (pad rows hold zeros)
+    int row_a, rows_a;                           // A = features [row_a, row_a + rows_a) (G_* numbering), rows_a = 128 or 256
+    int row_b, rows_b;                           // B features, staged in whole blocks of 64, <= 256
+    int n_b;                                     // MMA N: the valid B features rounded up to 16 (pad features hold zeros)
     int n_slabs;                                 // samples / 64
     float *partial;                              // [gridDim.x][rows_a][rows_b]
     float *dbias;                                // optional: dbias[n] += sum_s A[n][s]
@@ -87,19 +89,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer
-        const uint32_t idesc = idesc_bf16(128, (uint32_t)a.rows_b);
+        const uint32_t idesc = idesc_bf16_mn(128, (uint32_t)a.n_b);
         for (int c = 0; c < my_slabs; ++c) {
             const int s = c % kStages, use = c / kStages;
             wait(bar(B_FULL + s), use & 1);
             tc_fence_after_sync();
             if (elect_one()) {
-                const uint64_t adesc = smem_desc_sw128(sm_base + s * kStage);
-                const uint64_t bdesc = smem_desc_sw128(sm_base + s * kStage + kTileA);
-                for (int mb = 0; mb < m_blocks; ++mb)
+                const uint64_t adesc = smem_desc_sw128_mn(sm_base + s * kStage, 8192);
+                const uint64_t bdesc = smem_desc_sw128_mn(sm_base + s * kStage + kTileA, 8192);
+                for (int mb = 0; mb < m_blocks; ++mb)         // 128 output features = two blocks; 16 samples = 2048 B
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_bf16_ss(tmem_base + mb * 256, adesc + (uint64_t)((mb * 16384) >> 4) + 2 * k, bdesc + 2 * k, idesc,
-                                    (c | k) != 0);
+                        mma_bf16_ss(tmem_base + mb * 256, adesc + (uint64_t)((mb * 16384 + k * 2048) >> 4),
+                                    bdesc + (uint64_t)((k * 2048) >> 4), idesc, (c | k) != 0);
                 mma_commit(bar(B_EMPTY + s));
                 if (c == my_slabs - 1) mma_commit(bar(B_DONE));
             }
@@ -107,8 +109,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;                       // 8 warps
-        // ---------------- bias gradients: thread t sums row t of every staged A tile (all eight 16-byte units of
-        // the row, so the swizzle does not matter; lanes start at rotated units to spread the banks)
+        // ---------------- bias gradients: thread t sums feature t of every staged A tile (a warp reads 32 consecutive
+        // features of one sample per step: conflict-free)
         if (want_bias) {
             const int t = ew * 32 + lane;
             float bs = 0.f;
@@ -116,14 +118,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                 const int s = c % kStages, use = c / kStages;
                 wait(bar(B_FULL + s), use & 1);
                 if (t < a.rows_a) {
-                    const uint32_t rowp = sm_base + s * kStage + t * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 v = ld_shared_f4(rowp + (((j + lane) & 7) << 4));
-                        const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) bs += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
-                    }
+                    const unsigned short *blk = reinterpret_cast<const unsigned short *>(sm + s * kStage + (t >> 6) * 8192);
+                    const int u = (t & 63) >> 3, e = t & 7;
+#pragma unroll 16
+                    for (int k = 0; k < 64; ++k)
+                        bs += __uint_as_float((uint32_t)blk[k * 64 + ((u ^ (k & 7)) << 3) + e] << 16);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_EMPTY + s));
@@ -138,8 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
         if (ew < 4 * m_blocks) {
             const int mb = ew >> 2, q = warp & 3;      // TMEM lane quadrant = warp % 4
             const int n = mb * 128 + q * 32 + lane;
-            float *dst = a.partial + ((size_t)blockIdx.x * a.rows_a + n) * a.rows_b;
-            for (int col = 0; col < a.rows_b; col += 32) {
+            float *dst = a.partial + ((size_t)blockIdx.x * a.rows_a + n) * a.n_b;
+            for (int col = 0; col < a.n_b; col += 32) {
                 uint32_t v[32];
                 if (my_slabs > 0) {
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mb * 256 + col, v);
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    if (col + i < a.rows_b)
+                    if (col + i < a.n_b)
                         *reinterpret_cast<uint4 *>(dst + col + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
         }
@@ -174,16 +173,19 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int split
 }
 
 // Skinny weight gradients (density head: 1 output row; colour layer 1: 3): dW[a][k] += sum_s A[a][s] B[k][s],
-// dbias[a] += sum_s A[a][s].  A is fp32 [row][ch]; B is a slab-major bf16 operand group.  A block walks slabs:
-// it stages the slab's contiguous B tile (coalesced 16-byte loads) and the 64 A values per row in shared memory,
-// thread k takes the dot products of B row k, and the block's totals go out as one atomicAdd per element.
+// dbias[a] += sum_s A[a][s].  A is fp32 [row][ch]; B is a group of bf16 operand blocks (train_layout.h).  A block
+// walks slabs: it stages the slab's contiguous B tile (coalesced 16-byte loads) and the 64 A values per row in
+// shared memory, thread k takes the dot products of B feature k, and the block's totals go out as one atomicAdd
+// per element.
 __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, int ch,
                                                            const __nv_bfloat16 *__restrict__ ws, int row_b, int rows_b,
                                                            float *__restrict__ dW, int ld, float *__restrict__ dbias)
 {
-    __shared__ __align__(16) uint4 tile[256 * 8];          // [rows_b][8 units], swizzled as stored
+    __shared__ __align__(16) uint4 tile[256 * 8];          // [block][sample][64 features], swizzled as stored
     __shared__ __align__(16) float as[4][64];
     const int k = threadIdx.x, n_slabs = ch / 64;
+    const unsigned short *blk = reinterpret_cast<const unsigned short *>(tile) + (k >> 6) * 4096;
+    const int u = (k & 63) >> 3, e = k & 7;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, bs = 0.f;
     for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
         const uint4 *src = reinterpret_cast<const uint4 *>(ws + big_tile(row_b, slab));
@@ -194,21 +196,12 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restri
         }
         __syncthreads();
         if (k < rows_b) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int p = (j + k) & 7;                 // rotated start: conflict-free 16-byte reads
-                const uint4 v = tile[k * 8 + p];
-                const int g = p ^ (k & 7);                 // sample group held by unit p of row k
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll 8
+            for (int s = 0; s < 64; ++s) {
+                const float b = __uint_as_float((uint32_t)blk[s * 64 + ((u ^ (s & 7)) << 3) + e] << 16);
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    if (r < rows_a) {
-                        const float4 a0 = reinterpret_cast<const float4 *>(as[r])[2 * g], a1 = reinterpret_cast<const float4 *>(as[r])[2 * g + 1];
-                        acc[r] += (a0.x * __uint_as_float(w[0] << 16) + a0.y * __uint_as_float(w[0] & 0xffff0000u)) +
-                                  (a0.z * __uint_as_float(w[1] << 16) + a0.w * __uint_as_float(w[1] & 0xffff0000u)) +
-                                  (a1.x * __uint_as_float(w[2] << 16) + a1.y * __uint_as_float(w[2] & 0xffff0000u)) +
-                                  (a1.z * __uint_as_float(w[3] << 16) + a1.w * __uint_as_float(w[3] & 0xffff0000u));
-                    }
+                    if (r < rows_a) acc[r] = fmaf(as[r][s], b, acc[r]);
             }
         }
         if (dbias && threadIdx.x >= 224 && threadIdx.x - 224 < rows_a) {   // bias: the last warp's first lanes
@@ -230,7 +223,7 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restri
 int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld,
                  float *dbias, cudaStream_t stream)
 {
-    if (rows_a > 4 || rows_b > 256) return NERF_B200_EINVAL;
+    if (rows_a > 4 || rows_b > 256 || (row_b & 63)) return NERF_B200_EINVAL;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -241,14 +234,16 @@ int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, in
 
 size_t wgrad_tc_scratch_bytes(int splits) { return (size_t)splits * 256 * 256 * sizeof(float); }
 
-// dW (+)= A-by-B^T over the chunk's samples on the tensor cores; A and B are row groups of the slab-major bf16
-// operand rows at `ws`.
+// dW (+)= A-by-B^T over the chunk's samples on the tensor cores; A and B are feature groups (G_* numbering, starting
+// on a block boundary) of the bf16 operand blocks at `ws`.
 int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
              float *dbias, float *scratch, int splits, cudaStream_t stream)
 {
     wg::Args a = {};
     a.ws = ws; a.row_a = row_a; a.rows_a = rows_a; a.row_b = row_b;
-    a.rows_b = (rows_b_valid + 15) / 16 * 16;
+    a.rows_b = (rows_b_valid + 63) / 64 * 64;
+    a.n_b = (rows_b_valid + 15) / 16 * 16;
+    if ((row_a | row_b | rows_a) & 63) return NERF_B200_EINVAL;
     a.n_slabs = ch / 64; a.partial = scratch; a.dbias = dbias;
     if (splits > a.n_slabs) splits = a.n_slabs;
     cudaError_t e = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
@@ -257,7 +252,7 @@ int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows
     int rc = launch_status();
     if (rc) return rc;
     const int total = rows_a * rows_b_valid;
-    wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.rows_b, rows_b_valid, dW, ld, col_off);
+    wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.n_b, rows_b_valid, dW, ld, col_off);
     return launch_status();
 }
 
