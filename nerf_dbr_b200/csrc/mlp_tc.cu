@@ -461,13 +461,8 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
             if (lane == 0) mbar_arrive(bar_ready);
             // exactly what the next layer multiplies: the bf16-rounded values (128 contiguous bytes per sample)
             store_block_row(ws_out, ws_row, ws_col, pk);
-            unsigned long long bits = 0ull;      // + the ReLU mask of these 64 activations for the dgrad chain
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                bits |= (unsigned long long)((pk[i] & 0xffffu) != 0u) << (2 * i);
-                bits |= (unsigned long long)((pk[i] >> 16) != 0u) << (2 * i + 1);
-            }
-            *mask_out = bits;
+            // + the ReLU mask of these 64 activations for the dgrad chain
+            *mask_out = (unsigned long long)relu_mask_word(pk) | ((unsigned long long)relu_mask_word(pk + 16) << 32);
             return;
         }
     } else {
@@ -562,9 +557,8 @@ __device__ __forceinline__ void train_heads_row(uint32_t t_row, uint32_t rayb_ad
             r[2] = fmaf(v[0], w2.x, r[2]); r[2] = fmaf(v[1], w2.y, r[2]); r[2] = fmaf(v[2], w2.z, r[2]); r[2] = fmaf(v[3], w2.w, r[2]);
             pk[2 * i] = pack_bf16(v[0], v[1]);
             pk[2 * i + 1] = pack_bf16(v[2], v[3]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mbits[g] |= (unsigned int)(v[j] > 0.f) << (4 * i + j);
         }
+        mbits[g] = relu_mask_word(pk);
         if (col >= 0) {                                     // 32 features = four 16-byte units of this sample's row
             uint4 *rowp = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(ws) + big_row(G_C0H + 64 * (g >> 1), col));
 #pragma unroll

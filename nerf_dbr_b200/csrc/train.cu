@@ -26,7 +26,7 @@
 
 namespace nerfb200 {
 
-constexpr int kChunkSamples = 262144;        // samples per chunk (multiple of 64): 4.7 GB of workspace at most
+constexpr int kChunkSamples = 524288;        // samples per chunk (multiple of 64): 9.5 GB of workspace at most
 constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per SM over the chunk's samples
 
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,

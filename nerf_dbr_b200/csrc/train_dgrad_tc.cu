@@ -164,16 +164,13 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     tmem_ld32(t_cols, xa);
                     tmem_ld32(t_cols + 32, xb);
                     tmem_ld_wait();
-                    const unsigned long long m = on ? mbits[hh] : 0ull;      // ReLU mask of these 64 activations
+                    const uint32_t m_lo = on ? (uint32_t)mbits[hh] : 0u, m_hi = on ? (uint32_t)(mbits[hh] >> 32) : 0u;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        // bf16 pairs: the values wgrad multiplies are exactly the ones the next GEMM of the chain sees
-                        const float a0 = (m >> (2 * i)) & 1ull ? __uint_as_float(xa[2 * i]) : 0.f;
-                        const float a1 = (m >> (2 * i + 1)) & 1ull ? __uint_as_float(xa[2 * i + 1]) : 0.f;
-                        const float b0 = (m >> (32 + 2 * i)) & 1ull ? __uint_as_float(xb[2 * i]) : 0.f;
-                        const float b1 = (m >> (33 + 2 * i)) & 1ull ? __uint_as_float(xb[2 * i + 1]) : 0.f;
-                        pk[i] = pack_bf16(a0, a1);
-                        pk[16 + i] = pack_bf16(b0, b1);
+                        // bf16 pairs: the values wgrad multiplies are exactly the ones the next GEMM of the chain sees;
+                        // dpre = dh where the forward's activation was > 0 (train_layout.h: relu_mask_word)
+                        pk[i] = pack_bf16(__uint_as_float(xa[2 * i]), __uint_as_float(xa[2 * i + 1])) & relu_pair_mask(m_lo, i);
+                        pk[16 + i] = pack_bf16(__uint_as_float(xb[2 * i]), __uint_as_float(xb[2 * i + 1])) & relu_pair_mask(m_hi, i);
                     }
                     if (g < kDgGemms - 1) {                                // hand the operand to the next GEMM first
                         tmem_st32(t_cols, pk);
@@ -219,11 +216,9 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                     const float4 w2 = ld_shared_f4(wc1 + 1024 + (64 * kb + 4 * i) * 4);
                     float v[4] = {dy[0] * w0.x + dy[1] * w1.x + dy[2] * w2.x, dy[0] * w0.y + dy[1] * w1.y + dy[2] * w2.y,
                                   dy[0] * w0.z + dy[1] * w1.z + dy[2] * w2.z, dy[0] * w0.w + dy[1] * w1.w + dy[2] * w2.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (!((mc0[kb] >> (4 * i + j)) & 1ull)) v[j] = 0.f;
-                    pk[2 * i] = pack_bf16(v[0], v[1]);
-                    pk[2 * i + 1] = pack_bf16(v[2], v[3]);
+                    const uint32_t mw = (2 * i) >> 4 ? (uint32_t)(mc0[kb] >> 32) : (uint32_t)mc0[kb];
+                    pk[2 * i] = pack_bf16(v[0], v[1]) & relu_pair_mask(mw, (2 * i) & 15);
+                    pk[2 * i + 1] = pack_bf16(v[2], v[3]) & relu_pair_mask(mw, (2 * i + 1) & 15);
                 }
                 if (on) store_block_row(a.ws, G_DPREC0 + 64 * kb, col, pk);
                 tmem_st32(t_row + 64 * kb, pk);

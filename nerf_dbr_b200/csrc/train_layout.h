@@ -15,8 +15,8 @@ constexpr int R_DSIG = R_RGB + 3;            // 1    dL/d sigma_pre
 constexpr int R_DY = R_DSIG + 1;             // 3    dL/d colour pre-sigmoid
 constexpr int R_DPRE = R_DY + 3;             // 8 x 256   dL/d pre-activation of trunk layers
 constexpr int R_DPREC0 = R_DPRE + 8 * 256;   // 128
-// ReLU masks written by the tensor-core forward (bit j of word (layer, part) = activation 64*part + j > 0), so the
-// dgrad chain reads 8 bytes per thread and half instead of 64 strided floats: uint64 [(layer*4 + part)][ch]
+// ReLU masks written by the tensor-core forward, so the dgrad chain reads 8 bytes per thread and half instead of 64
+// activations: uint64 [(layer*4 + part)][ch], one 32-bit word per 32 features (relu_mask_word below)
 constexpr int R_MASK = R_DPREC0 + 128;       // 8 layers x 4 parts x 2 floats (one uint64 per sample)
 constexpr int R_MASKC0 = R_MASK + 64;        // colour layer 0: 2 parts x 2 floats
 constexpr int R_TOTAL = R_MASKC0 + 4;
@@ -55,6 +55,22 @@ __host__ __device__ constexpr int big_feature(int r)
 }
 
 #ifdef __CUDACC__
+// ReLU mask of 32 post-ReLU activations held as 16 bf16 pairs (all >= +0): pair i's flags land at bit i (even
+// feature) and bit 16 + i (odd feature).  h + 0x7fff carries into bit 15 exactly when h != 0: 3 instructions a pair.
+__device__ __forceinline__ uint32_t relu_mask_word(const uint32_t *pk)
+{
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc |= ((pk[i] + 0x7fff7fffu) >> (15 - i)) & (0x00010001u << i);
+    return acc;
+}
+// ... and the AND-mask (0xffff per active half) of pair i: shift the flags to the byte sign bits, replicate them
+__device__ __forceinline__ uint32_t relu_pair_mask(uint32_t word, int i)
+{
+    uint32_t r;                                  // prmt selector nibble 8 | b: replicate the sign bit of byte b
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word << (15 - i)), "r"(0u), "r"(0xBB99u));
+    return r;
+}
 // one sample's 64 features of one block: eight 16-byte stores (pk[4u .. 4u+3] = features 8u .. 8u+7 as bf16 pairs)
 __device__ __forceinline__ void store_block_row(void *ws, int g0, int col, const uint32_t (&pk)[32], int units = 8)
 {
