@@ -85,7 +85,8 @@ constexpr uint32_t SM_DE = SM_RAYB + 8192;                 // [8][32] f32      d
 constexpr uint32_t SM_SCR = SM_DE + 1024;                  // back-warp scratch (256 B)
 constexpr uint32_t SM_BAR = SM_SCR + 256;                  // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+constexpr uint32_t SM_STAGE = SM_TMEM + 256;               // TRAIN: 8 x 2 KB store staging, one per epilogue warp
+constexpr uint32_t SM_TOTAL = SM_STAGE + 16384;
 constexpr uint32_t kSmemBytes = SM_TOTAL + 1024;           // + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -438,12 +439,12 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
     }
 }
 
-// ws_out (TRAIN): bf16 operand rows of the workspace (or nullptr); ws_row = first feature row of this warp's 64,
-// ws_col = this thread's sample
+// ws_out (TRAIN): bf16 operand blocks of the workspace (or nullptr); ws_row = first feature of this warp's 64;
+// col_r / stage: see store_block_rows_staged (train_layout.h); mask_out = this thread's mask word or nullptr
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
-                                              unsigned short *ws_out = nullptr, int ws_row = 0, int ws_col = 0,
-                                              unsigned long long *mask_out = nullptr)
+                                              unsigned short *ws_out = nullptr, int ws_row = 0, const int *col_r = nullptr,
+                                              uint32_t stage = 0, unsigned long long *mask_out = nullptr)
 {
     uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
@@ -460,9 +461,10 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready);
             // exactly what the next layer multiplies: the bf16-rounded values (128 contiguous bytes per sample)
-            store_block_row(ws_out, ws_row, ws_col, pk);
+            const int cr[4] = {col_r[0], col_r[1], col_r[2], col_r[3]};
+            store_block_rows_staged(ws_out, ws_row, cr, pk, stage, lane);
             // + the ReLU mask of these 64 activations for the dgrad chain
-            *mask_out = (unsigned long long)relu_mask_word(pk) | ((unsigned long long)relu_mask_word(pk + 16) << 32);
+            if (mask_out) *mask_out = (unsigned long long)relu_mask_word(pk) | ((unsigned long long)relu_mask_word(pk + 16) << 32);
             return;
         }
     } else {
@@ -739,6 +741,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         uint32_t g = 0;
         for (int t = 0; t < my_tiles; ++t) {
             long long *tr = (a.trace && blockIdx.x == 0 && t < kTraceTiles && ew == 0 && lane == 0) ? a.trace + t * 72 : nullptr;
+            int col = -1, col_r[4] = {-1, -1, -1, -1};
+            if (TRAIN) {
+                col = ws_col(a, row_info(a, tile_begin + t, row));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) col_r[j] = __shfl_sync(0xffffffffu, col, (lane >> 2) + 8 * j);
+            }
             for (int layer = 0; layer < 8; ++layer, ++g) {
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
 #pragma unroll
@@ -748,17 +756,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     if (tr) tr[layer * 8 + (hh == 0 ? 3 : 6)] = clock64();
                     unsigned short *ws_out = nullptr;
                     unsigned long long *mask_out = nullptr;
-                    int col = -1;
                     if (TRAIN) {
-                        col = ws_col(a, row_info(a, tile_begin + t, row));
-                        if (col >= 0) {
-                            ws_out = reinterpret_cast<unsigned short *>(a.ws);
+                        ws_out = reinterpret_cast<unsigned short *>(a.ws);
+                        if (col >= 0)
                             mask_out = reinterpret_cast<unsigned long long *>(a.ws + (size_t)R_MASK * a.ws_ch) +
                                        (size_t)(layer * 4 + hh * 2 + w2) * a.ws_ch + col;
-                        }
                     }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
-                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, G_H + layer * 256 + hh * 128 + 64 * w2, col, mask_out);
+                                         bar(B_AREADY + 2 * hh + w2), lane, ws_out, G_H + layer * 256 + hh * 128 + 64 * w2, col_r,
+                                         sm_base + SM_STAGE + ew * 2048, mask_out);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();

@@ -32,7 +32,8 @@ constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_WC1 = kSlots * kSlotBytes;              // [3][128] f32
 constexpr uint32_t SM_BAR = SM_WC1 + 1536;
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t kSmem = SM_TMEM + 16 + 1024;
+constexpr uint32_t SM_STAGE = SM_TMEM + 256;                      // 8 x 2 KB store staging, one per epilogue warp
+constexpr uint32_t kSmem = SM_STAGE + 16384 + 1024;
 
 enum { B_WFULL = 0, B_WEMPTY = 4, B_ACCFULL = 8, B_AREADY = 10, B_R1FREE = 14, B_COUNT = 15 };
 // a_ready[kb]: phase g of a tile = K-block kb of GEMM g's A operand is in TMEM (g = 0: written by the front warps,
@@ -146,6 +147,12 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
         for (int t = 0; t < my_tiles; ++t) {
             const int col = (tile_begin + t) * 128 + row;
             const bool on = col < a.n_samples_total;
+            int col_r[4];                                                  // the rows this lane writes back (staged stores)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (tile_begin + t) * 128 + q * 32 + (lane >> 2) + 8 * j;
+                col_r[j] = c < a.n_samples_total ? c : -1;
+            }
             for (int g = 0; g < kDgGemms; ++g) {
                 const int layer = 7 - g;                                   // dh of trunk layer `layer`
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
                     }
-                    if (on) store_block_row(a.ws, G_DPRE + layer * 256 + n0, col, pk);   // 128 contiguous bytes per sample
+                    store_block_rows_staged(a.ws, G_DPRE + layer * 256 + n0, col_r, pk, sm_base + SM_STAGE + ew * 2048, lane);
                 }
             }
             // region 1 (G7's accumulator) has been read: the next tile's G0 operand may be written there

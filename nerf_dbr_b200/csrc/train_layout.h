@@ -55,6 +55,38 @@ __host__ __device__ constexpr int big_feature(int r)
 }
 
 #ifdef __CUDACC__
+// Warp-cooperative version for the hot epilogues: lane l holds the 64 features of the sample in row l of the warp's
+// 32 rows.  Storing them directly makes every store instruction touch 32 different lines with 16 bytes each (half a
+// sector: the L2 sees one partial-sector write per lane).  Going through a 2 KB warp-private staging buffer, four
+// units at a time, each store instruction instead writes 8 rows x 64 contiguous bytes -- whole sectors only.
+// col_r[j] = workspace sample of row (lane >> 2) + 8 j (or -1), i.e. the rows this lane writes back.
+__device__ __forceinline__ void store_block_rows_staged(void *ws, int g0, const int (&col_r)[4], const uint32_t (&pk)[32],
+                                                        uint32_t stage, int lane)
+{
+    const uint32_t wr = stage + lane * 64, sx = (lane >> 1) & 3;
+    const int q = lane & 3;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; ++p)                    // slot p of row `lane` (rotated: conflict-free both ways)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((p ^ sx) << 4)), "r"(pk[16 * ph + 4 * p]),
+                         "r"(pk[16 * ph + 4 * p + 1]), "r"(pk[16 * ph + 4 * p + 2]), "r"(pk[16 * ph + 4 * p + 3]) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = (lane >> 2) + 8 * j;
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stage + r * 64 + (((q ^ (r >> 1)) & 3) << 4)) : "memory");
+            if (col_r[j] >= 0) {
+                uint4 *row = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(ws) + big_row(g0, col_r[j]));
+                row[(4 * ph + q) ^ (col_r[j] & 7)] = v;
+            }
+        }
+    }
+}
+
 // ReLU mask of 32 post-ReLU activations held as 16 bf16 pairs (all >= +0): pair i's flags land at bit i (even
 // feature) and bit 16 + i (odd feature).  h + 0x7fff carries into bit 15 exactly when h != 0: 3 instructions a pair.
 __device__ __forceinline__ uint32_t relu_mask_word(const uint32_t *pk)
