@@ -160,15 +160,32 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
 }
 
 // grads[n][col_off + k] += sum_split partial[split][n][k]   (k < rows_b_valid)
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int rows_a, int rows_b, int rows_b_valid,
-                                    float *__restrict__ dW, int ld, int col_off)
+// A block owns 64 consecutive elements of the [rows_a][rows_b] partial; its four thread groups each take every
+// fourth split with four loads in flight (the partials were just written: they sit in L2, latency is the cost).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int rows_a, int rows_b,
+                                                           int rows_b_valid, float *__restrict__ dW, int ld, int col_off)
 {
-    const int total = rows_a * rows_b_valid;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int n = i / rows_b_valid, k = i % rows_b_valid;
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)sp * rows_a + n) * rows_b + k];
-        dW[(size_t)n * ld + col_off + k] += s;
+    __shared__ float part[4][64];
+    const int o = threadIdx.x & 63, sg = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + o, total = rows_a * rows_b;
+    const size_t stride = (size_t)rows_a * rows_b;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < total) {
+        const float *p = partial + i;
+        int sp = sg;
+        for (; sp + 12 < splits; sp += 16) {
+            s0 += __ldg(p + (size_t)sp * stride);
+            s1 += __ldg(p + (size_t)(sp + 4) * stride);
+            s2 += __ldg(p + (size_t)(sp + 8) * stride);
+            s3 += __ldg(p + (size_t)(sp + 12) * stride);
+        }
+        for (; sp < splits; sp += 4) s0 += __ldg(p + (size_t)sp * stride);
+    }
+    part[sg][o] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (sg == 0 && i < total) {
+        const int n = i / rows_b, k = i % rows_b;
+        if (k < rows_b_valid) dW[(size_t)n * ld + col_off + k] += (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
     }
 }
 
@@ -251,8 +268,7 @@ int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows
     wg::wgrad_tc_kernel<<<splits, wg::kThreads, wg::kSmem, stream>>>(a);
     int rc = launch_status();
     if (rc) return rc;
-    const int total = rows_a * rows_b_valid;
-    wg::wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(scratch, splits, rows_a, a.n_b, rows_b_valid, dW, ld, col_off);
+    wg::wgrad_reduce_kernel<<<(rows_a * a.n_b + 63) / 64, 256, 0, stream>>>(scratch, splits, rows_a, a.n_b, rows_b_valid, dW, ld, col_off);
     return launch_status();
 }
 
