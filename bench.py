@@ -156,6 +156,25 @@ def run_reference(args):
     emit(line)
 
 
+def train_roofline(precision, n_samples, flop, ms):
+    """Step-level roofline of the training workload.  BF16 mode is HBM-bound by construction: the forward writes the
+    bf16 operand blocks (4544 B/sample + 88 B of masks and head rows), the dgrad chain writes dpre (4352 B, reads
+    88 B), the eleven wgrad launches read every operand once (9600 B), the ray kernel 36 B -- 18.7 KB per sample
+    (DESIGN.md 4.3).  Pure-write streams top out at 3.9 TB/s on this part (tools/probe/hbm_write_bw.py), reads at
+    6.9 TB/s, so the floor of this traffic mix is about 0.70 of the copy-bandwidth peak reported here."""
+    tfl = flop / (ms * 1e-3) / 1e12
+    if precision != "bf16":
+        return {"bound": "tensor", "achieved": tfl, "peak": peaks()["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": tfl / peaks()["bf16_tflops"], "traffic": None, "note": "FP32 CUDA-core kernels (gradient parity mode)"}
+    bytes_per_sample = 4544 + 88 + 4352 + 88 + 9600 + 36
+    gbs = bytes_per_sample * n_samples / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks()["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks()["hbm_gbs"],
+            "traffic": None, "algorithmic_bytes_per_sample": bytes_per_sample, "tflops": tfl,
+            "tflops_frac_of_bf16_peak": tfl / peaks()["bf16_tflops"],
+            "note": ("whole step: forward, dgrad chain and wgrad on tcgen05 (bf16 operands, fp32 accumulate); activations and "
+                     "pre-activation gradients visit HBM once as bf16; write-only streams peak at 3.9 TB/s on this part")}
+
+
 def run_train(args):
     """BASELINE.json configs[3]: 4096-ray batch, coarse 64 jittered + fine 128 uniform samples, forward + backward of
     mse(coarse)+mse(fine), data-parallel (ray batch sharded, one NCCL gradient all-reduce) + Adam step.  Not the
@@ -222,11 +241,7 @@ def run_train(args):
               "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
                          "loss_last": float(loss)},
               "gpu_launches": int(ops.launch_count() - n0),
-              "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peaks()["bf16_tflops"],
-                           "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peaks()["bf16_tflops"], "traffic": None,
-                           "note": ("forward, dgrad chain and wgrad on tcgen05 (bf16 operands, fp32 accumulate); activations "
-                                    "round-trip HBM between the three phases" if args.precision == "bf16"
-                                    else "FP32 CUDA-core kernels (gradient parity mode)")}})
+              "roofline": train_roofline(args.precision, n_rays * (n_c + n_f), flop, ms)})
     if world > 1:
         dist.destroy_process_group()
 

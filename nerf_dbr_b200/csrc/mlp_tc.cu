@@ -894,6 +894,7 @@ int tc_train_forward(const void *packed, const float *rays_o, const float *rays_
     a.n_rays = n_rays; a.n_samples = n_samples;
     a.near = near; a.far = far;
     a.ws = ws; a.ws_ch = ws_ch; a.dbg = dbg;
+    a.trace = g_tc_trace;
     return tc::launch<tc::SRC_RAYS, false, true>(a, stream);
 }
 

@@ -362,6 +362,32 @@ static int sm_count()
     return sms;
 }
 
+// BF16 mode runs the per-tensor wgrad launches (independent of each other) alternately on two auxiliary streams:
+// every launch has ~19 us of fixed cost (ramp, pipeline fill, partial write-out, tail, then its reduce) during
+// which HBM idles; with two streams the next tensor's CTAs take over SMs as the previous one's drain.  Forked from
+// and joined back into the caller's stream with events, one set per device.
+struct WgradStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+static WgradStreams *wgrad_streams()
+{
+    static WgradStreams per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    WgradStreams &w = per_dev[dev];
+    if (!w.ok) {
+        bool good = cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && good; ++i)
+            good = cudaStreamCreateWithFlags(&w.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&w.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!good) { cudaGetLastError(); return nullptr; }
+        w.ok = true;
+    }
+    return &w;
+}
+
 static int chunk_rays(int n_samples)
 {
     int r = kChunkSamples / n_samples;
@@ -379,7 +405,7 @@ size_t nerf_b200_train_workspace_bytes(int n_rays, int n_samples)
     if (n_rays <= 0 || n_samples <= 0) return 0;
     long long per = (long long)std::min(n_rays, chunk_rays(n_samples)) * n_samples;
     long long ch = (per + 63) / 64 * 64;
-    return (size_t)ch * R_TOTAL * sizeof(float) + wgrad_tc_scratch_bytes(kWgradSplits);
+    return (size_t)ch * R_TOTAL * sizeof(float) + 2 * wgrad_tc_scratch_bytes(kWgradSplits);   // one scratch per wgrad stream
 }
 
 int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, const nerf_b200_params *grads,
@@ -449,16 +475,27 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         auto row = [&](int r) { return ws + (size_t)r * ch; };
         const int split = std::max(1, std::min(64, (int)(ch / 2048)));
         float *scratch = ws + (size_t)R_TOTAL * ch;
+        WgradStreams *wst = tc ? wgrad_streams() : nullptr;
+        if (tc && !wst) return (int)cudaErrorUnknown;
+        int n_wgrad = 0;
+        cudaError_t ce;
+        if (tc) {                                       // fork: both wgrad streams wait for the dgrad chain
+            if ((ce = cudaEventRecord(wst->fork, stream)) != cudaSuccess) return (int)ce;
+            for (int i = 0; i < 2; ++i)
+                if ((ce = cudaStreamWaitEvent(wst->s[i], wst->fork, 0)) != cudaSuccess) return (int)ce;
+        }
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
             if (tc) {
                 // BF16 mode: the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
                 const int row_a = big_feature((int)((A - ws) / ch)), row_b = big_feature((int)((B - ws) / ch));
+                const int si = n_wgrad++ & 1;
                 if (rows_a <= 4)
-                    return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db), stream);
+                    return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db), wst->s[si]);
                 return wgrad_tc(wsb, row_a, rows_a, row_b, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
-                                const_cast<float *>(db), scratch, kWgradSplits, stream);
+                                const_cast<float *>(db), scratch + (size_t)si * (wgrad_tc_scratch_bytes(kWgradSplits) / sizeof(float)),
+                                kWgradSplits, wst->s[si]);
             }
             dim3 grid((rows_a + 63) / 64, (rows_b + 63) / 64, split);
             wgrad_kernel<<<grid, 256, 0, stream>>>(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
@@ -475,6 +512,11 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         if ((rc = wgrad(row(R_DPREC0), 128, row(R_H + 256 * 7), 256, g.color0_w, 283, 0, g.color0_b))) return rc;
         if ((rc = wgrad(row(R_DPREC0), 128, row(R_DE), 27, g.color0_w, 283, 256, nullptr))) return rc;
         if ((rc = wgrad(row(R_DY), 3, row(R_C0H), 128, g.color1_w, 128, 0, g.color1_b))) return rc;
+        if (tc)                                         // join: the caller's stream continues after both
+            for (int i = 0; i < 2; ++i)
+                if ((ce = cudaEventRecord(wst->join[i], wst->s[i])) != cudaSuccess ||
+                    (ce = cudaStreamWaitEvent(stream, wst->join[i], 0)) != cudaSuccess)
+                    return (int)ce;
     }
     return 0;
 }

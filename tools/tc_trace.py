@@ -10,11 +10,25 @@ dev = torch.device("cuda", 0)
 z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
 net = ops.pack_weights({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev)
 pose = O.benchmark_pose(1, 40)
-ops.render_image(net, pose, 800, 600, 128, mode=1)
+TRAIN = len(sys.argv) > 1 and sys.argv[1] == "train"      # timeline of the TRAIN forward variant instead
+if TRAIN:
+    import nerf_dbr_b200 as nb
+    model = nb.NeRFModel().to(dev)
+    g = torch.Generator().manual_seed(0)
+    ro = torch.zeros(4096, 3) + torch.tensor([0.0, 0.0, 4.0])
+    rd = torch.nn.functional.normalize(torch.randn(4096, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+    tgt = torch.rand(4096, 3, generator=g)
+
+    def run():
+        ops.train_fwd_bwd(model, ro.to(dev), rd.to(dev), tgt.to(dev), 128, mode=L.BF16)
+else:
+    def run():
+        ops.render_image(net, pose, 800, 600, 128, mode=1)
+run()
 torch.cuda.synchronize()
 buf = torch.zeros(6 * 9 * 8, dtype=torch.int64, device=dev)
 L.load_library().nerf_b200_set_trace_buffer(ctypes.c_void_p(buf.data_ptr()))
-ops.render_image(net, pose, 800, 600, 128, mode=1)
+run()
 torch.cuda.synchronize()
 L.load_library().nerf_b200_set_trace_buffer(None)
 t = buf.cpu().numpy().reshape(6, 9, 8).astype(np.int64)
