@@ -197,7 +197,8 @@ def run_train(args):
     coarse, fine = nb.NeRFModel().to(dev), nb.NeRFModel().to(dev)
     coarse.load_state_dict(ck["coarse_model"]); fine.load_state_dict(ck["fine_model"])
     from nerf_dbr_b200.host import lib as L
-    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32)
+    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32,
+                         overlap=args.overlap, overlap_sms=args.overlap_sms)
     opt = torch.optim.Adam(step.parameters(), lr=5e-4)
     pose = torch.eye(4); pose[2, 3] = 4.0
     ro, rd = O.camera_rays(pose, 200, 150)
@@ -249,6 +250,8 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--overlap-sms", type=int, default=64, help="train workload: SMs given to the overlapped weight-gradient phase")
+    ap.add_argument("--overlap", action="store_true", help="train workload: software-pipeline the passes (B200TrainStep overlap=True)")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

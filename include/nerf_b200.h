@@ -174,6 +174,21 @@ NERF_B200_API int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_pa
                             int mode, void *workspace, float *loss_sum, float *rgb_out,
                             void *stream);
 
+/* Split form for callers that overlap the two networks of a step (B200TrainStep): the activation phase of one
+ * network (forward, compositing backward, dgrad chain -- bound by HBM *writes*) can run beside the weight-gradient
+ * phase of the other (bound by HBM *reads*) on disjoint SMs.  `phases`: ACTIVATIONS leaves everything the
+ * weight-gradient phase needs in `workspace`; WEIGHT_GRADS consumes it (same arguments, same workspace, later on
+ * any stream ordered after the first call) and accumulates into `grads`; ALL = both = nerf_b200_train_fwd_bwd.
+ * Split phases need mode BF16 and a batch that fits one workspace chunk (524288 samples), else
+ * NERF_B200_EUNSUPPORTED.  `sm_limit` > 0 caps the CTAs of every launch of this call (0 = all SMs). */
+enum { NERF_B200_TRAIN_ACTIVATIONS = 1, NERF_B200_TRAIN_WEIGHT_GRADS = 2, NERF_B200_TRAIN_ALL = 3 };
+NERF_B200_API int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *params_dev_ptrs_host,
+                               const nerf_b200_params *grads_dev_ptrs_host, const float *rays_o,
+                               const float *rays_d, const float *target, int n_rays, int n_samples,
+                               float near, float far, const float *t_rand, int n_rays_global,
+                               int mode, void *workspace, float *loss_sum, float *rgb_out,
+                               int phases, int sm_limit, void *stream);
+
 /* ---- introspection (tests / bench) -------------------------------------------------------
  * Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 NERF_B200_API uint64_t nerf_b200_launch_count(void);

@@ -121,6 +121,7 @@ struct Args {
     float *ws;                 // TRAIN: training workspace [R_TOTAL][ws_ch] (train_layout.h); rays are chunk-local
     int ws_ch;
     unsigned int *dbg;         // optional: [0] = first timeout code
+    int sm_limit;              // 0 = every SM; else at most this many CTAs (the caller runs something else beside)
     long long *trace;          // optional timeline (tools/tc_trace.py): CTA 0, first kTraceTiles tiles
 };
 constexpr int kTraceTiles = 6;
@@ -818,6 +819,7 @@ static int plan(Args &a)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (a.sm_limit > 0 && a.sm_limit < sms) sms = a.sm_limit;
     const int S = a.n_samples;
     if (S < 1 || S > 32768) return NERF_B200_EUNSUPPORTED;
     if (S <= kTileM) {
@@ -886,9 +888,10 @@ int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d,
 // Training forward on the tensor cores: rays [0, n_rays) of the given (chunk-local) arrays; activations, head
 // outputs and encodings go to the workspace (train_layout.h) for the ray kernel, the dgrad chain and wgrad.
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
-                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream)
+                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, int sm_limit, cudaStream_t stream)
 {
     tc::Args a = {};
+    a.sm_limit = sm_limit;
     a.packed = reinterpret_cast<const unsigned char *>(packed);
     a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
     a.n_rays = n_rays; a.n_samples = n_samples;

@@ -30,9 +30,9 @@ constexpr int kChunkSamples = 524288;        // samples per chunk (multiple of 6
 constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per SM over the chunk's samples
 
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
-                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, cudaStream_t stream);
-int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, cudaStream_t stream);
-int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias,
+                     float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, int sm_limit, cudaStream_t stream);
+int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, int sm_limit, cudaStream_t stream);
+int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias, int sm_limit,
                  cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
 int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
@@ -413,7 +413,23 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
                             int n_samples, float near, float far, const float *t_rand, int n_rays_global,
                             int mode, void *workspace, float *loss_sum, float *rgb_out, void *stream_)
 {
+    return nerf_b200_train_fwd_bwd_ex(packed, params, grads, rays_o, rays_d, target, n_rays, n_samples, near, far, t_rand,
+                                      n_rays_global, mode, workspace, loss_sum, rgb_out, NERF_B200_TRAIN_ALL, 0, stream_);
+}
+
+int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *params, const nerf_b200_params *grads,
+                               const float *rays_o, const float *rays_d, const float *target, int n_rays,
+                               int n_samples, float near, float far, const float *t_rand, int n_rays_global,
+                               int mode, void *workspace, float *loss_sum, float *rgb_out, int phases, int sm_limit,
+                               void *stream_)
+{
     (void)params;
+    if (phases != NERF_B200_TRAIN_ALL && phases != NERF_B200_TRAIN_ACTIVATIONS && phases != NERF_B200_TRAIN_WEIGHT_GRADS)
+        return NERF_B200_EINVAL;
+    if (sm_limit < 0) return NERF_B200_EINVAL;
+    // split phases keep the activations in the workspace between two calls: BF16 mode, one chunk
+    if (phases != NERF_B200_TRAIN_ALL && (mode != NERF_B200_BF16 || n_rays > chunk_rays(n_samples > 0 ? n_samples : 1)))
+        return NERF_B200_EUNSUPPORTED;
     if (!packed || !grads || !rays_o || !rays_d || !target || !workspace || !loss_sum || n_rays <= 0 ||
         n_samples <= 0 || n_rays_global <= 0)
         return NERF_B200_EINVAL;
@@ -442,6 +458,7 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
         a.loss_sum = loss_sum; a.rgb_out = rgb_out;
         const int tiles = a.ch / TM;
         int rc;
+        if (phases & NERF_B200_TRAIN_ACTIVATIONS) {
         if (tc) {
             // forward on the tensor cores (TRAIN variant of the fused kernel); pad columns of the stored
             // activations must be finite zeros: wgrad multiplies them by zero gradients
@@ -450,7 +467,7 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
                 cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)G_TOTAL * 128, stream);
             const float *tr = t_rand ? t_rand + (size_t)r0 * n_samples : nullptr;
             if ((rc = tc_train_forward(packed, rays_o + 3 * (size_t)r0, rays_d + 3 * (size_t)r0, a.n_rays, n_samples, near, far,
-                                       tr, a.ws, a.ch, nullptr, stream)))
+                                       tr, a.ws, a.ch, nullptr, sm_limit, stream)))
                 return rc;
         } else {
             train_fwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
@@ -465,11 +482,13 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
                 cudaMemset2DAsync(a.ws + (size_t)R_DSIG * a.ch + n_smp, (size_t)a.ch * sizeof(float), 0,
                                   (size_t)(a.ch - n_smp) * sizeof(float), 4, stream);       // dsig, dy (fp32 rows)
             }
-            if ((rc = dgrad_chain_tc(packed, a.ws, a.ch, n_smp, nullptr, stream))) return rc;
+            if ((rc = dgrad_chain_tc(packed, a.ws, a.ch, n_smp, nullptr, sm_limit, stream))) return rc;
         } else {
             train_bwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
             if ((rc = launch_status())) return rc;
         }
+        }                                               // phase: activations
+        if (!(phases & NERF_B200_TRAIN_WEIGHT_GRADS)) continue;
         float *ws = a.ws;
         const size_t ch = a.ch;
         auto row = [&](int r) { return ws + (size_t)r * ch; };
@@ -490,12 +509,13 @@ int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, 
                 // BF16 mode: the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
                 const int row_a = big_feature((int)((A - ws) / ch)), row_b = big_feature((int)((B - ws) / ch));
-                const int si = n_wgrad++ & 1;
+                const int si = sm_limit > 0 ? 0 : n_wgrad++ & 1;      // SM-limited: the caller overlaps something else; stay narrow
                 if (rows_a <= 4)
-                    return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db), wst->s[si]);
+                    return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db),
+                                        sm_limit, wst->s[si]);
                 return wgrad_tc(wsb, row_a, rows_a, row_b, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
                                 const_cast<float *>(db), scratch + (size_t)si * (wgrad_tc_scratch_bytes(kWgradSplits) / sizeof(float)),
-                                kWgradSplits, wst->s[si]);
+                                sm_limit > 0 ? std::min(kWgradSplits, sm_limit) : kWgradSplits, wst->s[si]);
             }
             dim3 grid((rows_a + 63) / 64, (rows_b + 63) / 64, split);
             wgrad_kernel<<<grid, 256, 0, stream>>>(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,

@@ -255,11 +255,12 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
 }  // namespace dg
 
 // dgrad chain over the chunk's samples (columns [0, n_samples) of the workspace; `ch` = pitch, multiple of 64)
-int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, cudaStream_t stream)
+int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, int sm_limit, cudaStream_t stream)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
     dg::Args a = {};
     a.packed = reinterpret_cast<const unsigned char *>(packed);
     a.ws = ws; a.ch = ch; a.n_samples_total = n_samples; a.dbg = dbg;

@@ -238,12 +238,13 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restri
 }  // namespace wg
 
 int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld,
-                 float *dbias, cudaStream_t stream)
+                 float *dbias, int sm_limit, cudaStream_t stream)
 {
     if (rows_a > 4 || rows_b > 256 || (row_b & 63)) return NERF_B200_EINVAL;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
     const int grid = std::min(ch / 64, 4 * sms);
     wg::wgrad_skinny_kernel<<<grid, 256, 0, stream>>>(A, rows_a, ch, ws, row_b, rows_b, dW, ld, dbias);
     return launch_status();

@@ -13,6 +13,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libnerf_b200.so")
 
 FP32, BF16, BF16X3 = 0, 1, 2
+TRAIN_ACTIVATIONS, TRAIN_WEIGHT_GRADS, TRAIN_ALL = 1, 2, 3      # nerf_b200_train_fwd_bwd_ex phases
 
 _lib = None
 
@@ -60,6 +61,9 @@ PROTOTYPES = {
     "nerf_b200_train_fwd_bwd": (c_int, [c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Params), c_void_p,
                                         c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_int,
                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nerf_b200_train_fwd_bwd_ex": (c_int, [c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Params), c_void_p,
+                                           c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_int,
+                                           c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "nerf_b200_launch_count": (c_uint64, []),
     "nerf_b200_set_watchdog_word": (None, [c_void_p]),
     "nerf_b200_set_trace_buffer": (None, [c_void_p]),

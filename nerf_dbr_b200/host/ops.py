@@ -219,6 +219,55 @@ def render_hierarchical(coarse_packed, fine_packed, rays_o, rays_d, n_coarse: in
 _workspaces = {}
 
 
+class TrainPass:
+    """One network's forward + backward over one ray batch, prepared once and run in one or two phases
+    (``nerf_b200_train_fwd_bwd_ex``): ``run(L.TRAIN_ALL)``, or ``run(L.TRAIN_ACTIVATIONS)`` followed -- possibly
+    on another stream, ordered after it -- by ``run(L.TRAIN_WEIGHT_GRADS)``.  ``slot`` selects the cached
+    workspace: passes whose phases overlap in time need different slots."""
+
+    def __init__(self, model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_rays_global: Optional[int] = None,
+                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True, slot: int = 0, packed=None):
+        self.lib = L.load_library()
+        self.ro, self.rd, self.tg = (_dev(x, "train_fwd_bwd") for x in (rays_o, rays_d, target))
+        self.n, self.n_samples, self.near, self.far, self.mode = self.ro.shape[0], n_samples, near, far, mode
+        self.n_global = self.n if n_rays_global is None else n_rays_global
+        dev = self.dev = self.ro.device
+        named = dict(model.named_parameters())
+        params, grads = {}, {}
+        for k in STATE_ORDER:
+            p = named[k]
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise L.NerfB200Error("train_fwd_bwd", -101, f"parameter {k} must be a contiguous fp32 CUDA tensor")
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            params[k], grads[k] = p.detach(), p.grad
+        self.packed = pack_weights(params, dev) if packed is None else packed
+        nbytes = self.lib.nerf_b200_train_workspace_bytes(self.n, n_samples)
+        ws = _workspaces.get((dev, slot))
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _workspaces[(dev, slot)] = ws
+        self.ws = ws
+        self.loss_sum = torch.zeros(1, device=dev)
+        self.rgb = torch.empty(self.n, 3, device=dev) if want_rgb else None
+        self.tr = None if t_rand is None else _dev(t_rand, "train_fwd_bwd")
+        self.ps, self.gs = params_struct(params), params_struct(grads)
+        self._keep = (params, grads)
+
+    def run(self, phases: int = L.TRAIN_ALL, sm_limit: int = 0) -> "TrainPass":
+        with torch.cuda.device(self.dev):
+            L.check("nerf_b200_train_fwd_bwd_ex", self.lib.nerf_b200_train_fwd_bwd_ex(
+                _ptr(self.packed), ctypes.byref(self.ps), ctypes.byref(self.gs), _ptr(self.ro), _ptr(self.rd), _ptr(self.tg),
+                self.n, self.n_samples, self.near, self.far, _ptr(self.tr), self.n_global, self.mode, _ptr(self.ws),
+                _ptr(self.loss_sum), _ptr(self.rgb), phases, sm_limit, _stream()))
+        return self
+
+    @property
+    def loss(self):
+        """This pass's loss term: sum of squared errors over its rays with the global normaliser."""
+        return self.loss_sum[0] / (3.0 * self.n_global)
+
+
 def train_fwd_bwd(model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_rays_global: Optional[int] = None,
                   near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True):
     """Forward + backward of one network's loss term mean((C - target)^2) (reference
@@ -226,35 +275,8 @@ def train_fwd_bwd(model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_
     reference's parameter names); d loss/d params is accumulated into ``p.grad`` (created as zeros when
     None) -- scaled for ``n_rays_global`` rays so data-parallel ranks can all-reduce-sum.  Returns
     (loss_term as a 0-dim tensor computed over this call's rays with the global normaliser, rgb [R,3])."""
-    lib = L.load_library()
-    ro, rd, tg = _dev(rays_o, "train_fwd_bwd"), _dev(rays_d, "train_fwd_bwd"), _dev(target, "train_fwd_bwd")
-    n = ro.shape[0]
-    n_global = n if n_rays_global is None else n_rays_global
-    dev = ro.device
-    named = dict(model.named_parameters())
-    params, grads = {}, {}
-    for k in STATE_ORDER:
-        p = named[k]
-        if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-            raise L.NerfB200Error("train_fwd_bwd", -101, f"parameter {k} must be a contiguous fp32 CUDA tensor")
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-        params[k], grads[k] = p.detach(), p.grad
-    packed = pack_weights(params, dev)
-    nbytes = lib.nerf_b200_train_workspace_bytes(n, n_samples)
-    ws = _workspaces.get(dev)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _workspaces[dev] = ws
-    loss_sum = torch.zeros(1, device=dev)
-    rgb = torch.empty(n, 3, device=dev) if want_rgb else None
-    tr = None if t_rand is None else _dev(t_rand, "train_fwd_bwd")
-    ps, gs = params_struct(params), params_struct(grads)
-    with torch.cuda.device(dev):
-        L.check("nerf_b200_train_fwd_bwd", lib.nerf_b200_train_fwd_bwd(
-            _ptr(packed), ctypes.byref(ps), ctypes.byref(gs), _ptr(ro), _ptr(rd), _ptr(tg), n, n_samples, near, far,
-            _ptr(tr), n_global, mode, _ptr(ws), _ptr(loss_sum), _ptr(rgb), _stream()))
-    return loss_sum[0] / (3.0 * n_global), rgb
+    tp = TrainPass(model, rays_o, rays_d, target, n_samples, t_rand, n_rays_global, near, far, mode, want_rgb).run()
+    return tp.loss, tp.rgb
 
 
 def launch_count() -> int:
