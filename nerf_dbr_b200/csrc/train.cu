@@ -35,8 +35,7 @@ int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigne
 int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias, int sm_limit,
                  cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
-int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
-             float *dbias, float *scratch, int splits, cudaStream_t stream);
+int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_jobs, float *scratch, int ctas, cudaStream_t stream);
 
 struct TrainArgs {
     const float *wf;                         // fp32 region of the packed weights
@@ -405,7 +404,7 @@ size_t nerf_b200_train_workspace_bytes(int n_rays, int n_samples)
     if (n_rays <= 0 || n_samples <= 0) return 0;
     long long per = (long long)std::min(n_rays, chunk_rays(n_samples)) * n_samples;
     long long ch = (per + 63) / 64 * 64;
-    return (size_t)ch * R_TOTAL * sizeof(float) + 2 * wgrad_tc_scratch_bytes(kWgradSplits);   // one scratch per wgrad stream
+    return (size_t)ch * R_TOTAL * sizeof(float) + wgrad_tc_scratch_bytes(256);                // partials of one batched wgrad launch
 }
 
 int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, const nerf_b200_params *grads,
@@ -496,26 +495,27 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
         float *scratch = ws + (size_t)R_TOTAL * ch;
         WgradStreams *wst = tc ? wgrad_streams() : nullptr;
         if (tc && !wst) return (int)cudaErrorUnknown;
-        int n_wgrad = 0;
         cudaError_t ce;
         if (tc) {                                       // fork: both wgrad streams wait for the dgrad chain
             if ((ce = cudaEventRecord(wst->fork, stream)) != cudaSuccess) return (int)ce;
             for (int i = 0; i < 2; ++i)
                 if ((ce = cudaStreamWaitEvent(wst->s[i], wst->fork, 0)) != cudaSuccess) return (int)ce;
         }
+        // BF16 mode: the tensor-core jobs of the chunk are collected and go out as ONE launch (+ one reduce) on
+        // auxiliary stream 0; the two skinny head gradients run beside it on auxiliary stream 1
+        WgradJob jobs[16];
+        int n_jobs = 0;
         auto wgrad = [&](const float *A, int rows_a, const float *B, int rows_b, const float *dW, int ld, int col_off,
                          const float *db) -> int {
             if (tc) {
-                // BF16 mode: the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
+                // the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
                 const int row_a = big_feature((int)((A - ws) / ch)), row_b = big_feature((int)((B - ws) / ch));
-                const int si = sm_limit > 0 ? 0 : n_wgrad++ & 1;      // SM-limited: the caller overlaps something else; stay narrow
                 if (rows_a <= 4)
                     return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db),
-                                        sm_limit, wst->s[si]);
-                return wgrad_tc(wsb, row_a, rows_a, row_b, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
-                                const_cast<float *>(db), scratch + (size_t)si * (wgrad_tc_scratch_bytes(kWgradSplits) / sizeof(float)),
-                                sm_limit > 0 ? std::min(kWgradSplits, sm_limit) : kWgradSplits, wst->s[si]);
+                                        sm_limit, wst->s[1]);
+                jobs[n_jobs++] = WgradJob{row_a, rows_a, row_b, rows_b, const_cast<float *>(dW), ld, col_off, const_cast<float *>(db)};
+                return 0;
             }
             dim3 grid((rows_a + 63) / 64, (rows_b + 63) / 64, split);
             wgrad_kernel<<<grid, 256, 0, stream>>>(A, rows_a, B, rows_b, (int)ch, const_cast<float *>(dW), ld, col_off,
@@ -532,11 +532,15 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
         if ((rc = wgrad(row(R_DPREC0), 128, row(R_H + 256 * 7), 256, g.color0_w, 283, 0, g.color0_b))) return rc;
         if ((rc = wgrad(row(R_DPREC0), 128, row(R_DE), 27, g.color0_w, 283, 256, nullptr))) return rc;
         if ((rc = wgrad(row(R_DY), 3, row(R_C0H), 128, g.color1_w, 128, 0, g.color1_b))) return rc;
-        if (tc)                                         // join: the caller's stream continues after both
-            for (int i = 0; i < 2; ++i)
+        if (tc) {
+            if ((rc = wgrad_tc_batch(reinterpret_cast<const __nv_bfloat16 *>(ws), (int)ch, jobs, n_jobs, scratch,
+                                     sm_limit > 0 ? std::min(sms, sm_limit) : sms, wst->s[0])))
+                return rc;
+            for (int i = 0; i < 2; ++i)                 // join: the caller's stream continues after both
                 if ((ce = cudaEventRecord(wst->join[i], wst->s[i])) != cudaSuccess ||
                     (ce = cudaStreamWaitEvent(stream, wst->join[i], 0)) != cudaSuccess)
                     return (int)ce;
+        }
     }
     return 0;
 }

@@ -54,6 +54,14 @@ __host__ __device__ constexpr int big_feature(int r)
     return r < R_SIGPRE ? (r < R_DE ? r : G_DE + (r - R_DE)) : G_DPRE + (r - R_DPRE);
 }
 
+// one tensor-core weight-gradient job: dW[n][col_off + k] += sum_s A[n][s] B[k][s], dbias[n] += sum_s A[n][s]
+struct WgradJob {
+    int row_a, rows_a, row_b, rows_b_valid;      // feature groups in G_* numbering
+    float *dW;
+    int ld, col_off;
+    float *dbias;                                // or nullptr
+};
+
 #ifdef __CUDACC__
 // Warp-cooperative version for the hot epilogues: lane l holds the 64 features of the sample in row l of the warp's
 // 32 rows.  Storing them directly makes every store instruction touch 32 different lines with 16 bytes each (half a

@@ -34,14 +34,31 @@ constexpr uint32_t kSmem = SM_TMEM + 16 + 1024;
 
 enum { B_FULL = 0, B_EMPTY = kStages, B_DONE = 2 * kStages };
 
-struct Args {
-    const __nv_bfloat16 *ws;                     // bf16 operand rows (slab-major)
+constexpr int kMaxJobs = 16;
+
+// One launch covers every tensor of a chunk: CTA b works for job j with cta_begin[j] <= b < cta_begin[j + 1] on the
+// (b - cta_begin[j])-th part of the slab range.  CTAs are apportioned to jobs by operand bytes (host side).
+struct Job {
     int row_a, rows_a;                           // A = features [row_a, row_a + rows_a) (G_* numbering), rows_a = 128 or 256
     int row_b, rows_b;                           // B features, staged in whole blocks of 64, <= 256
     int n_b;                                     // MMA N: the valid B features rounded up to 16 (pad features hold zeros)
-    int n_slabs;                                 // samples / 64
-    float *partial;                              // [gridDim.x][rows_a][rows_b]
+    float *partial;                              // [splits][rows_a][n_b]
     float *dbias;                                // optional: dbias[n] += sum_s A[n][s]
+};
+struct Args {
+    const __nv_bfloat16 *ws;                     // bf16 operand blocks
+    int n_slabs;                                 // samples / 64
+    int n_jobs;
+    int cta_begin[kMaxJobs + 1];
+    Job job[kMaxJobs];
+};
+struct ReduceArgs {                              // block b reduces 64 elements of job j, blk_begin[j] <= b < blk_begin[j + 1]
+    int n_jobs;
+    int blk_begin[kMaxJobs + 1];
+    const float *partial[kMaxJobs];
+    int splits[kMaxJobs], rows_a[kMaxJobs], n_b[kMaxJobs], rows_b_valid[kMaxJobs];
+    float *dW[kMaxJobs];
+    int ld[kMaxJobs], col_off[kMaxJobs];
 };
 
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
@@ -51,15 +68,19 @@ __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
         if (clock64() - t0 > 4000000000LL) __trap();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ Args args)
 {
+    int j = 0;
+    while (j + 1 < args.n_jobs && (int)blockIdx.x >= args.cta_begin[j + 1]) ++j;
+    const Job &a = args.job[j];
+    const int split = blockIdx.x - args.cta_begin[j], splits = args.cta_begin[j + 1] - args.cta_begin[j];
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_base = smem_u32(sm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) { return sm_base + SM_BAR + 8u * i; };
-    const int per = (a.n_slabs + gridDim.x - 1) / gridDim.x;
-    const int c_begin = blockIdx.x * per, c_end = min(a.n_slabs, c_begin + per);
+    const int per = (args.n_slabs + splits - 1) / splits;
+    const int c_begin = split * per, c_end = min(args.n_slabs, c_begin + per);
     const int my_slabs = max(0, c_end - c_begin);
     const bool want_bias = a.dbias != nullptr;
 
@@ -83,8 +104,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
                 const int s = c % kStages, use = c / kStages;
                 if (use > 0) wait(bar(B_EMPTY + s), (use - 1) & 1);
                 mbar_arrive_expect_tx(bar(B_FULL + s), bytes_a + bytes_b);
-                bulk_g2s(sm_base + s * kStage, a.ws + big_tile(a.row_a, c_begin + c), bytes_a, bar(B_FULL + s));
-                bulk_g2s(sm_base + s * kStage + kTileA, a.ws + big_tile(a.row_b, c_begin + c), bytes_b, bar(B_FULL + s));
+                bulk_g2s(sm_base + s * kStage, args.ws + big_tile(a.row_a, c_begin + c), bytes_a, bar(B_FULL + s));
+                bulk_g2s(sm_base + s * kStage + kTileA, args.ws + big_tile(a.row_b, c_begin + c), bytes_b, bar(B_FULL + s));
             }
         }
     } else if (warp == 1) {
@@ -137,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
         if (ew < 4 * m_blocks) {
             const int mb = ew >> 2, q = warp & 3;      // TMEM lane quadrant = warp % 4
             const int n = mb * 128 + q * 32 + lane;
-            float *dst = a.partial + ((size_t)blockIdx.x * a.rows_a + n) * a.n_b;
+            float *dst = a.partial + ((size_t)split * a.rows_a + n) * a.n_b;
             for (int col = 0; col < a.n_b; col += 32) {
                 uint32_t v[32];
                 if (my_slabs > 0) {
@@ -159,19 +180,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Args a)
     if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<512>(tmem_base); }
 }
 
-// grads[n][col_off + k] += sum_split partial[split][n][k]   (k < rows_b_valid)
-// A block owns 64 consecutive elements of the [rows_a][rows_b] partial; its four thread groups each take every
+// grads[n][col_off + k] += sum_split partial[split][n][k]   (k < rows_b_valid), every job of the chunk in one launch.
+// A block owns 64 consecutive elements of a job's [rows_a][n_b] partial; its four thread groups each take every
 // fourth split with four loads in flight (the partials were just written: they sit in L2, latency is the cost).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int rows_a, int rows_b,
-                                                           int rows_b_valid, float *__restrict__ dW, int ld, int col_off)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceArgs r)
 {
     __shared__ float part[4][64];
+    int j = 0;
+    while (j + 1 < r.n_jobs && (int)blockIdx.x >= r.blk_begin[j + 1]) ++j;
+    const int rows_a = r.rows_a[j], rows_b = r.n_b[j], splits = r.splits[j];
     const int o = threadIdx.x & 63, sg = threadIdx.x >> 6;
-    const int i = blockIdx.x * 64 + o, total = rows_a * rows_b;
+    const int i = (blockIdx.x - r.blk_begin[j]) * 64 + o, total = rows_a * rows_b;
     const size_t stride = (size_t)rows_a * rows_b;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (i < total) {
-        const float *p = partial + i;
+        const float *p = r.partial[j] + i;
         int sp = sg;
         for (; sp + 12 < splits; sp += 16) {
             s0 += __ldg(p + (size_t)sp * stride);
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
     __syncthreads();
     if (sg == 0 && i < total) {
         const int n = i / rows_b, k = i % rows_b;
-        if (k < rows_b_valid) dW[(size_t)n * ld + col_off + k] += (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
+        if (k < r.rows_b_valid[j]) r.dW[j][(size_t)n * r.ld[j] + r.col_off[j] + k] += (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
     }
 }
 
@@ -250,26 +273,64 @@ int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, in
     return launch_status();
 }
 
-size_t wgrad_tc_scratch_bytes(int splits) { return (size_t)splits * 256 * 256 * sizeof(float); }
+size_t wgrad_tc_scratch_bytes(int ctas) { return (size_t)(ctas + wg::kMaxJobs) * 256 * 256 * sizeof(float); }
 
-// dW (+)= A-by-B^T over the chunk's samples on the tensor cores; A and B are feature groups (G_* numbering, starting
-// on a block boundary) of the bf16 operand blocks at `ws`.
-int wgrad_tc(const __nv_bfloat16 *ws, int row_a, int rows_a, int row_b, int rows_b_valid, int ch, float *dW, int ld, int col_off,
-             float *dbias, float *scratch, int splits, cudaStream_t stream)
+// dW (+)= A-by-B^T over the chunk's samples on the tensor cores for every job in one launch, then one reduce launch.
+// A and B are feature groups (G_* numbering, starting on a block boundary) of the bf16 operand blocks at `ws`;
+// `ctas` CTAs are apportioned to the jobs by operand bytes (largest remainder, at least one each).
+int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_jobs, float *scratch, int ctas, cudaStream_t stream)
 {
+    if (n_jobs < 1 || n_jobs > wg::kMaxJobs) return NERF_B200_EINVAL;
     wg::Args a = {};
-    a.ws = ws; a.row_a = row_a; a.rows_a = rows_a; a.row_b = row_b;
-    a.rows_b = (rows_b_valid + 63) / 64 * 64;
-    a.n_b = (rows_b_valid + 15) / 16 * 16;
-    if ((row_a | row_b | rows_a) & 63) return NERF_B200_EINVAL;
-    a.n_slabs = ch / 64; a.partial = scratch; a.dbias = dbias;
-    if (splits > a.n_slabs) splits = a.n_slabs;
+    wg::ReduceArgs r = {};
+    a.ws = ws; a.n_slabs = ch / 64; a.n_jobs = r.n_jobs = n_jobs;
+    ctas = std::max(ctas, n_jobs);
+    int weight[wg::kMaxJobs], share[wg::kMaxJobs], total_w = 0, given = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const WgradJob &q = jobs[j];
+        if ((q.row_a | q.row_b | q.rows_a) & 63) return NERF_B200_EINVAL;
+        weight[j] = q.rows_a + (q.rows_b_valid + 63) / 64 * 64;
+        total_w += weight[j];
+    }
+    double frac[wg::kMaxJobs];
+    for (int j = 0; j < n_jobs; ++j) {
+        const double exact = (double)ctas * weight[j] / total_w;
+        share[j] = std::max(1, std::min(a.n_slabs, (int)exact));
+        frac[j] = exact - share[j];
+        given += share[j];
+    }
+    while (given < ctas) {                                            // largest remainder first
+        int best = -1;
+        for (int j = 0; j < n_jobs; ++j)
+            if (share[j] < a.n_slabs && (best < 0 || frac[j] > frac[best])) best = j;
+        if (best < 0) break;
+        ++share[best]; frac[best] -= 1.0; ++given;
+    }
+    size_t off = 0;
+    int blk = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const WgradJob &q = jobs[j];
+        wg::Job &d = a.job[j];
+        d.row_a = q.row_a; d.rows_a = q.rows_a; d.row_b = q.row_b;
+        d.rows_b = (q.rows_b_valid + 63) / 64 * 64;
+        d.n_b = (q.rows_b_valid + 15) / 16 * 16;
+        d.partial = scratch + off;
+        d.dbias = q.dbias;
+        a.cta_begin[j] = j ? a.cta_begin[j - 1] + share[j - 1] : 0;
+        r.blk_begin[j] = blk;
+        r.partial[j] = d.partial; r.splits[j] = share[j]; r.rows_a[j] = q.rows_a; r.n_b[j] = d.n_b;
+        r.rows_b_valid[j] = q.rows_b_valid; r.dW[j] = q.dW; r.ld[j] = q.ld; r.col_off[j] = q.col_off;
+        off += (size_t)share[j] * q.rows_a * d.n_b;
+        blk += (q.rows_a * d.n_b + 63) / 64;
+    }
+    a.cta_begin[n_jobs] = a.cta_begin[n_jobs - 1] + share[n_jobs - 1];
+    r.blk_begin[n_jobs] = blk;
     cudaError_t e = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::kSmem);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    wg::wgrad_tc_kernel<<<splits, wg::kThreads, wg::kSmem, stream>>>(a);
+    wg::wgrad_tc_kernel<<<a.cta_begin[n_jobs], wg::kThreads, wg::kSmem, stream>>>(a);
     int rc = launch_status();
     if (rc) return rc;
-    wg::wgrad_reduce_kernel<<<(rows_a * a.n_b + 63) / 64, 256, 0, stream>>>(scratch, splits, rows_a, a.n_b, rows_b_valid, dW, ld, col_off);
+    wg::wgrad_reduce_kernel<<<blk, 256, 0, stream>>>(r);
     return launch_status();
 }
 
