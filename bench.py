@@ -199,7 +199,7 @@ def run_train(args):
     from nerf_dbr_b200.host import lib as L
     step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32,
                          overlap=args.overlap, overlap_sms=args.overlap_sms)
-    opt = torch.optim.Adam(step.parameters(), lr=5e-4)
+    opt = torch.optim.Adam(step.parameters(), lr=5e-4, fused=True)      # the reference's optimizer, PyTorch's fused kernel
     pose = torch.eye(4); pose[2, 3] = 4.0
     ro, rd = O.camera_rays(pose, 200, 150)
     g = torch.Generator().manual_seed(0)

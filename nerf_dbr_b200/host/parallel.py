@@ -29,6 +29,9 @@ def allreduce_sum_(tensors: Iterable[torch.Tensor], extra: Optional[torch.Tensor
     tensors = list(tensors)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return extra
+    if len(tensors) == 1 and extra is None and tensors[0].is_contiguous():       # already a bucket: in place
+        dist.all_reduce(tensors[0], group=group)
+        return None
     parts = [t.reshape(-1) for t in tensors]
     if extra is not None:
         parts.append(extra.reshape(-1).to(parts[0].dtype))

@@ -14,6 +14,11 @@ from .model import NeRFModel
 from .parallel import allreduce_sum_
 
 
+def _world_size() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 class B200TrainStep:
     """Replaces NeRFTrainer._render_rays + loss + backward.  Data parallel: every rank passes its
     shard of the ray batch and the GLOBAL ray count; gradients are all-reduce-summed over NCCL.
@@ -35,6 +40,25 @@ class B200TrainStep:
         self.overlap, self.overlap_sms = overlap, overlap_sms
         self._side = None
         self._live = None
+        self._flat = None                            # one bucket: every gradient is a view of it, + 1 slot for the loss
+
+    def _attach_flat_grads(self):
+        """Gradients live in ONE flat fp32 buffer (each ``p.grad`` a view of it, like a DDP bucket): zeroing is one
+        memset, the data-parallel all-reduce runs in place on the bucket with no gather / scatter copies.  Re-attached
+        if someone replaced a ``.grad`` (e.g. ``optimizer.zero_grad(set_to_none=True)``)."""
+        params = self.parameters()
+        if not params[0].is_cuda:
+            return None
+        n = sum((p.numel() + 3) // 4 * 4 for p in params)      # every view starts 16-byte aligned
+        if self._flat is None or self._flat.device != params[0].device or self._flat.numel() != n + 4:
+            self._flat = torch.zeros(n + 4, device=params[0].device, dtype=torch.float32)
+        off = 0
+        for p in params:
+            view = self._flat[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr() or p.grad.shape != p.shape:
+                p.grad = view
+            off += (p.numel() + 3) // 4 * 4
+        return self._flat
 
     def parameters(self):
         return list(self.coarse.parameters()) + list(self.fine.parameters())
@@ -53,9 +77,13 @@ class B200TrainStep:
                  n_rays_global: Optional[int] = None, allreduce: bool = True):
         """Zeroes the gradients, runs forward+backward of both networks, all-reduces when a process
         group is initialised, returns (loss, rgb_coarse, rgb_fine)."""
-        grads = [p.grad for p in self.parameters() if p.grad is not None]
-        if grads:
-            torch._foreach_zero_(grads)              # one multi-tensor launch instead of 48 fills
+        flat = self._attach_flat_grads()
+        if flat is not None:
+            flat.zero_()                             # one memset for the 48 gradient tensors
+        else:
+            for p in self.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
         if t_rand is None:                       # the reference jitters the coarse samples (rendering.py:46)
             t_rand = torch.rand(rays_o.shape[0], self.n_coarse, device=rays_o.device)
         n = rays_o.shape[0]
@@ -66,8 +94,13 @@ class B200TrainStep:
             loss = lc + lf
         else:
             loss, rgb_c, rgb_f = self._pipeline(rays_o, rays_d, target, t_rand, kw)
-        if allreduce:
-            loss = allreduce_sum_([p.grad for p in self.parameters()], extra=loss)   # one 4.24 MB sum over NVLink
+        if allreduce and _world_size() > 1:
+            if flat is not None:                     # in place on the bucket (4.24 MB over NVLink); the loss rides in its last slot
+                flat[-1] = loss
+                allreduce_sum_([flat])
+                loss = flat[-1].clone()
+            else:
+                loss = allreduce_sum_([p.grad for p in self.parameters()], extra=loss)
         return loss, rgb_c, rgb_f
 
     def _pipeline(self, rays_o, rays_d, target, t_rand, kw):

@@ -44,6 +44,12 @@ def _worker(rank, world, port, out):
                 ref[i] += torch.randn(t.shape, generator=gr)
         loss = allreduce_sum_(grads, extra=torch.tensor(float(rank + 1)))
         ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(grads, ref)) and float(loss) == sum(range(1, world + 1))
+        # bucket form (B200TrainStep: every gradient is a view of one flat buffer, the loss rides in its last slot)
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        views = [flat[:6].view(2, 3), flat[6:9]]
+        assert allreduce_sum_([flat]) is None
+        tot = sum(range(1, world + 1))
+        ok = ok and torch.equal(views[0], (torch.arange(6, dtype=torch.float32) * tot).view(2, 3)) and float(flat[-1]) == 9.0 * tot
         # render shard: every rank fills its band with its rank id; gather on rank 0
         height, width = 7, 5
         row0, n = row_band(rank, world, height)
