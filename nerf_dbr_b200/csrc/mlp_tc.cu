@@ -295,7 +295,7 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 pk[i] = i < 16 ? pack_bf16(2 * i < kDirFeat ? de[q * 32 + 2 * i] : 0.f, 2 * i + 1 < kDirFeat ? de[q * 32 + 2 * i + 1] : 0.f) : 0u;
-            store_block_row(a.ws, G_DE, col, pk);
+            store_block_row(a.ws, G_DE, col, pk, 4);        // 32 features: wgrad multiplies N = 32 of this block
         }
     }
     named_bar_sync(1, 128);          // de[] is rewritten by the next produce
