@@ -112,7 +112,8 @@ NERF_B200_API int nerf_b200_positional_encoding(const float *x, int64_t n, int n
 
 /* query_network: BaseUnifiedRenderer.query_nerf_networks -> NeRFModel.forward
  * (base_renderer.py:165-188, src/models/nerf.py:92-131).  positions, directions [n,3] ->
- * sigma [n,1], rgb [n,3].  mode = NERF_B200_FP32 | NERF_B200_BF16. */
+ * sigma [n,1], rgb [n,3].  mode = NERF_B200_FP32 (CUDA cores) | NERF_B200_BF16 (the fused tcgen05 kernel with one
+ * (point, direction) pair per row; `packed` 1024-byte aligned).  BF16X3: NERF_B200_EUNSUPPORTED. */
 NERF_B200_API int nerf_b200_query_network(const void *packed, const float *positions, const float *directions,
                             int64_t n, int mode, float *sigma, float *rgb, void *stream);
 

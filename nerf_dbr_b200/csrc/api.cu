@@ -7,6 +7,7 @@ int simt_render_pose(const void *, const float *, int, int, float, float, float,
 int simt_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, const float *, float *, float *, float *, float *, cudaStream_t);
 int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, bool, float *, float *, unsigned int *, cudaStream_t);
 int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, const float *, bool, float *, float *, float *, float *, unsigned int *, cudaStream_t);
+int tc_query_points(const void *, const float *, const float *, long long, float *, float *, unsigned int *, cudaStream_t);
 }
 using namespace nerfb200;
 
@@ -23,8 +24,10 @@ int nerf_b200_query_network(const void *packed, const float *positions, const fl
 {
     if (!packed || !positions || !directions || !sigma || !rgb || n <= 0) return NERF_B200_EINVAL;
     if (mode == NERF_B200_FP32) return simt_query(packed, positions, directions, n, sigma, rgb, (cudaStream_t)stream);
-    // per-sample view directions need a per-row colour-0 operand; the tensor-core kernel takes the
-    // direction per ray (render_rays / render_image)
+    if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
+    // BF16: the fused tensor-core kernel with a (point, direction) pair per row; the direction part of colour layer 0
+    // is an fp32 per-row bias built by the back warps
+    if (mode == NERF_B200_BF16) return tc_query_points(packed, positions, directions, n, sigma, rgb, g_watchdog, (cudaStream_t)stream);
     return NERF_B200_EUNSUPPORTED;
 }
 

@@ -102,7 +102,7 @@ static_assert(B_COUNT * 8 <= 256, "barrier area");
 
 constexpr ChunkTable kChunks = make_chunk_table();
 
-enum { SRC_RAYS = 1, SRC_POSE = 2 };
+enum { SRC_RAYS = 1, SRC_POSE = 2, SRC_POINTS = 3 };   // SRC_POINTS: query_network -- a row is one (point, direction) pair
 
 struct Args {
     const unsigned char *packed;
@@ -110,6 +110,9 @@ struct Args {
     int width, row0;
     float half_w, half_h, focal;
     const float *rays_o, *rays_d, *t_rand;
+    const float *points, *dirs;                // SRC_POINTS: [n_points,3] each; outputs sigma_out [n_points], rgb_out [n_points,3]
+    float *sigma_out, *rgb_out;
+    int n_points;
     const float *z_vals;       // optional explicit depths [n_rays, n_samples] (ascending per ray)
     float *weights;            // optional per-sample compositing weights out [n_rays, n_samples]
     int n_rays, n_samples;
@@ -210,17 +213,20 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
                              const float *__restrict__ wf)
 {
     RowInfo ri = row_info(a, tile, row);
+    if (SRC == SRC_POINTS) ri.valid = tile * kTileM + row < a.n_points;
     float feat[64];
 #pragma unroll
     for (int f = 0; f < 64; ++f) feat[f] = 0.f;
     if (ri.valid) {
-        float o[3], d[3];
-        ray_of<SRC>(a, ri.ray, o, d);
-        float z = depth_of(a, ri.ray, ri.s, step);
+        float o[3], d[3], z = 0.f;
+        if (SRC != SRC_POINTS) {
+            ray_of<SRC>(a, ri.ray, o, d);
+            z = depth_of(a, ri.ray, ri.s, step);
+        }
         uint32_t ph[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float p = point_on_ray(o[c], d[c], z);
+            float p = SRC == SRC_POINTS ? __ldg(a.points + 3 * ((size_t)tile * kTileM + row) + c) : point_on_ray(o[c], d[c], z);
             feat[c] = p;
             ph[c] = phase_of(p);
         }
@@ -259,6 +265,7 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
                          pack_bf16(feat[8 * u + 4], feat[8 * u + 5]), pack_bf16(feat[8 * u + 6], feat[8 * u + 7]));
     }
 
+    if (SRC == SRC_POINTS) return;                         // per-row directions: the back warps build the colour-0 bias
     // direction encodings of the tile's rays: thread (q*32 + f) -> feature f of ray q (fp32, full-range sinf/cosf)
     const int rpt = a.tiles_per_ray == 1 ? (kTileM >> a.s_pad_log2) : 1;
     float *de = reinterpret_cast<float *>(sm + SM_DE);
@@ -527,6 +534,68 @@ __device__ __forceinline__ void color_row(uint32_t t_row, uint32_t rayb_addr, ui
     color_dot(xb, rayb_addr + 384, wc1_addr + 384, r0, r1, r2);
 }
 
+// SRC_POINTS back warps (query_network): this row's own view direction -> encoded direction (fp32, 27 registers) ->
+// colour layer 0's bias for each column on the fly (W_dir [27][128] and b_c0 sit in shared memory, read as
+// broadcasts), relu(acc + bias) . W_c1 -> sigmoid; density = relu(acc col 128 + b).  NeRFModel.forward's outputs.
+__device__ __forceinline__ void query_row(const Args &a, int idx, uint32_t t_row, uint32_t wdir_addr, uint32_t wc1_addr,
+                                          uint32_t bar_c0free, int lane, const float *__restrict__ wf)
+{
+    float de[kDirFeat];
+    const bool on = idx < a.n_points;
+    {
+        float d[3] = {0.f, 0.f, 0.f};
+        if (on)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = __ldg(a.dirs + 3 * (size_t)idx + c);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) de[c] = d[c];
+#pragma unroll
+        for (int k = 0; k < kDirFreq; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float arg = __fmul_rn(kPiF * (float)(1 << k), d[c]);
+                de[3 + 6 * k + c] = sinf(arg);
+                de[3 + 6 * k + 3 + c] = cosf(arg);
+            }
+    }
+    float r[3] = {0.f, 0.f, 0.f};
+    const uint32_t sg = tmem_ld1(t_row + 128);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t x[32];
+        tmem_ld32(t_row + 32 * g, x);
+        tmem_ld_wait();
+        if (g == 3) {                                       // the accumulator is in registers
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_c0free);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c0 = 32 * g + 4 * i;
+            float4 b = ld_shared_f4(wdir_addr + (kDirFeat * 128 + c0) * 4);          // b_c0
+#pragma unroll
+            for (int j = 0; j < kDirFeat; ++j) {
+                const float4 w = ld_shared_f4(wdir_addr + (j * 128 + c0) * 4);
+                b.x = fmaf(de[j], w.x, b.x); b.y = fmaf(de[j], w.y, b.y); b.z = fmaf(de[j], w.z, b.z); b.w = fmaf(de[j], w.w, b.w);
+            }
+            const float4 w0 = ld_shared_f4(wc1_addr + c0 * 4);
+            const float4 w1 = ld_shared_f4(wc1_addr + 512 + c0 * 4);
+            const float4 w2 = ld_shared_f4(wc1_addr + 1024 + c0 * 4);
+            const float v[4] = {fmaxf(__uint_as_float(x[4 * i + 0]) + b.x, 0.f), fmaxf(__uint_as_float(x[4 * i + 1]) + b.y, 0.f),
+                                fmaxf(__uint_as_float(x[4 * i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(x[4 * i + 3]) + b.w, 0.f)};
+            r[0] = fmaf(v[0], w0.x, r[0]); r[0] = fmaf(v[1], w0.y, r[0]); r[0] = fmaf(v[2], w0.z, r[0]); r[0] = fmaf(v[3], w0.w, r[0]);
+            r[1] = fmaf(v[0], w1.x, r[1]); r[1] = fmaf(v[1], w1.y, r[1]); r[1] = fmaf(v[2], w1.z, r[1]); r[1] = fmaf(v[3], w1.w, r[1]);
+            r[2] = fmaf(v[0], w2.x, r[2]); r[2] = fmaf(v[1], w2.y, r[2]); r[2] = fmaf(v[2], w2.z, r[2]); r[2] = fmaf(v[3], w2.w, r[2]);
+        }
+    }
+    if (on) {
+        a.sigma_out[idx] = fmaxf(__uint_as_float(sg) + __ldg(wf + F_BSIG), 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.rgb_out[3 * (size_t)idx + c] = 1.0f / (1.0f + expf(-(r[c] + __ldg(wf + F_BC1 + c))));
+    }
+}
+
 // TRAIN back warps: this row of colour layer 0's accumulator -> relu(acc + per-ray bias) stored as colour layer
 // 0's activation, colour pre-activations -> sigmoid -> stored, density pre-activation stored.  No compositing:
 // the training step's ray kernel does forward compositing, loss and backward in one pass.
@@ -693,6 +762,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         for (int i = threadIdx.x; i < 8 * 256; i += kThreads) bias[i] = __ldg(wf + F_BIAS + i);
         float *wc1 = reinterpret_cast<float *>(sm + SM_WC1);
         for (int i = threadIdx.x; i < 384; i += kThreads) wc1[i] = __ldg(wf + F_WC1 + i);
+        if (SRC == SRC_POINTS) {                           // W_dir [27][128] then b_c0 [128]: 14 KB of the staging region
+            float *wd = reinterpret_cast<float *>(sm + SM_STAGE);
+            for (int i = threadIdx.x; i < kDirFeat * 128; i += kThreads) wd[i] = __ldg(wf + F_WC0D + i);
+            for (int i = threadIdx.x; i < 128; i += kThreads) wd[kDirFeat * 128 + i] = __ldg(wf + F_BC0 + i);
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -793,7 +867,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             tc_fence_after_sync();
             const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
             const uint32_t t_row = tmem_base + ((uint32_t)((warp - 12) * 32) << 16) + (uint32_t)(t & 1) * 256;
-            if (TRAIN) {
+            if (SRC == SRC_POINTS) {
+                query_row(a, (tile_begin + t) * kTileM + row, t_row, sm_base + SM_STAGE, sm_base + SM_WC1, bar(B_C0FREE), lane, wf);
+            } else if (TRAIN) {
                 train_heads_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
                                 bar(B_C0FREE), lane, wf, a.ws, a.ws_ch, ws_col(a, row_info(a, tile_begin + t, row)));
             } else {
@@ -820,6 +896,10 @@ static int plan(Args &a)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (a.sm_limit > 0 && a.sm_limit < sms) sms = a.sm_limit;
+    if (a.n_points > 0) {                             // SRC_POINTS: a tile is 128 (point, direction) rows
+        a.n_samples = kTileM;
+        a.n_rays = (a.n_points + kTileM - 1) / kTileM;
+    }
     const int S = a.n_samples;
     if (S < 1 || S > 32768) return NERF_B200_EUNSUPPORTED;
     if (S <= kTileM) {
@@ -883,6 +963,19 @@ int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d,
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
     return split ? tc::launch<tc::SRC_RAYS, true>(a, stream) : tc::launch<tc::SRC_RAYS, false>(a, stream);
+}
+
+// NeRFModel.forward on (point, direction) rows: query_nerf_networks in BF16 mode
+int tc_query_points(const void *packed, const float *points, const float *dirs, long long n, float *sigma, float *rgb,
+                    unsigned int *dbg, cudaStream_t stream)
+{
+    if (n > (1ll << 30)) return NERF_B200_EUNSUPPORTED;
+    tc::Args a = {};
+    a.packed = reinterpret_cast<const unsigned char *>(packed);
+    a.points = points; a.dirs = dirs; a.n_points = (int)n;
+    a.sigma_out = sigma; a.rgb_out = rgb; a.dbg = dbg;
+    a.near = 0.f; a.far = 1.f;
+    return tc::launch<tc::SRC_POINTS, false>(a, stream);
 }
 
 // Training forward on the tensor cores: rays [0, n_rays) of the given (chunk-local) arrays; activations, head
