@@ -63,10 +63,11 @@ class B200Renderer(_Base):
                                  self.near, self.far)
 
     def query_nerf_networks(self, positions, directions, use_fine: bool = True):
-        """(density [N,1], rgb [N,3]) (base_renderer.py:165-188).  Per-sample directions run in the
-        FP32 kernel; the tensor-core kernel takes directions per ray (render_image)."""
+        """(density [N,1], rgb [N,3]) (base_renderer.py:165-188), one view direction per row.  'bf16': the fused
+        tensor-core kernel's (point, direction) variant; 'fp32' and 'bf16x3' (no split-precision variant of this
+        entry point): the FP32 CUDA-core kernel."""
         return ops.query_network(self._net(use_fine), positions.to(self._torch_device),
-                                 directions.to(self._torch_device), L.FP32)
+                                 directions.to(self._torch_device), L.BF16 if self.mode == L.BF16 else L.FP32)
 
     def execute_volume_rendering(self, densities, colors, z_vals, ray_directions) -> Tuple[torch.Tensor, torch.Tensor]:
         """(rgb_map [R,3], depth_map [R]) (pytorch_renderers.py:105-125)."""

@@ -106,6 +106,13 @@ def test_renderer_bf16_interface(checkpoints, tmp_path):
     assert rgb.shape == (48, 64, 3) and depth.shape == (48, 64)
     g = load_npz("golden_render.npz")
     check_bf16(rgb, depth, g["lego|bench1|64x48x16|rgb"], g["lego|bench1|64x48x16|depth"], "renderer")
+    # the reference's staged pipeline through the same object (generate_rays -> sample -> query -> composite) lands on
+    # the same image as the fused call
+    ro, rd = r.generate_rays(pose, 64, 48)
+    pts, z = r.sample_points_on_rays(ro.reshape(-1, 3), rd.reshape(-1, 3), 16)
+    dens, col = r.query_nerf_networks(pts.reshape(-1, 3), rd.reshape(-1, 1, 3).expand(-1, 16, -1).reshape(-1, 3).contiguous())
+    rgb2, depth2 = r.execute_volume_rendering(dens.reshape(-1, 16, 1), col.reshape(-1, 16, 3), z, rd.reshape(-1, 3))
+    assert (rgb2.reshape(48, 64, 3) - rgb).abs().max().item() <= 2e-5
 
 
 def test_bf16_repeated_launches_are_stable_and_deterministic(checkpoints, poses):
