@@ -69,3 +69,28 @@ def test_model_mirror_matches_reference_names(checkpoints):
     missing = m.load_state_dict(checkpoints["lego"]["fine_model"])
     assert not missing.missing_keys and not missing.unexpected_keys
     assert sum(p.numel() for p in m.parameters()) == 530052
+
+
+def test_argument_errors_return_codes_and_enqueue_nothing():
+    """include/nerf_b200.h: argument errors return negative NERF_B200_E* codes before anything is enqueued -- so they
+    can be exercised without a GPU.  (Pointers are never dereferenced on the host.)"""
+    import ctypes
+    from nerf_dbr_b200.host import lib as L
+    lib = L.load_library()
+    EINVAL, launches = -1, lib.nerf_b200_launch_count()
+    null = None
+    fake = ctypes.c_void_p(0x1000)
+    assert lib.nerf_b200_query_network(null, fake, fake, 8, L.BF16, fake, fake, null) == EINVAL
+    assert lib.nerf_b200_query_network(fake, fake, fake, 0, L.FP32, fake, fake, null) == EINVAL
+    assert lib.nerf_b200_positional_encoding(null, 4, 10, fake, null) == EINVAL
+    assert lib.nerf_b200_train_workspace_bytes(0, 64) == 0
+    ps = L.Params()
+    assert lib.nerf_b200_train_fwd_bwd_ex(fake, ctypes.byref(ps), ctypes.byref(ps), fake, fake, fake, 4, 64, 2.0, 6.0, null, 4,
+                                          L.BF16, fake, fake, null, 7, 0, null) == EINVAL          # phases not in {1, 2, 3}
+    assert lib.nerf_b200_train_fwd_bwd_ex(fake, ctypes.byref(ps), ctypes.byref(ps), fake, fake, fake, 4, 64, 2.0, 6.0, null, 4,
+                                          L.BF16, fake, fake, null, L.TRAIN_ALL, -1, null) == EINVAL   # negative SM limit
+    assert lib.nerf_b200_train_fwd_bwd_ex(fake, ctypes.byref(ps), ctypes.byref(ps), fake, fake, fake, 4, 64, 2.0, 6.0, null, 4,
+                                          L.FP32, fake, fake, null, L.TRAIN_ACTIVATIONS, 0, null) == -2  # split phases: BF16 only
+    for code in (-1, -2, -3):
+        assert lib.nerf_b200_error_string(code)
+    assert lib.nerf_b200_launch_count() == launches
