@@ -1,0 +1,150 @@
+"""Training loop on the B200 kernels with the reference trainer's interface and semantics
+(``NeRFTrainer``, src/training/trainer.py): same config keys, same batch format
+(``{'image': [H,W,3], 'pose': [4,4], 'focal': float}``), same per-step order -- random ray selection, coarse
+(stratified) + fine (uniform) render, ``mse + mse``, optional ``clip_grad_norm_``, Adam, exponential LR decay --
+same checkpoint format and resume rule.  What differs is where the work runs: rays, both networks' forward and
+backward and the full-image validation render are ``nerf_b200_*`` calls; optimizer, clipping and scheduler stay
+PyTorch on the same ``nn.Parameter``s (trainer.py:125-136).  Data parallel when ``torch.distributed`` is
+initialised: every rank draws the same ray selection, trains on its shard, gradients are all-reduced."""
+from __future__ import annotations
+
+import math
+import os
+import re
+from typing import Dict, Optional
+
+import torch
+
+from . import lib as L
+from . import ops
+from .model import NeRFModel
+from .parallel import ray_shard
+from .trainer import B200TrainStep, load_checkpoint, save_checkpoint
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class B200Trainer:
+    """Mirror of ``NeRFTrainer`` (trainer.py:18-81).  ``config`` keys read: hidden_dim / position_encoding_levels /
+    direction_encoding_levels (must be the reference's 256 / 10 / 4: the kernels are specialised for that network),
+    lr, weight_decay, lr_decay, decay_steps, n_coarse, n_fine, n_rays, near, far, gradient_clipping,
+    checkpoint_frequency, plus ``precision`` ('bf16' | 'fp32'), ``device_index``, ``seed``,
+    ``checkpoint_dir`` (default 'checkpoints', as the reference)."""
+
+    def __init__(self, config: Dict):
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Trainer needs a CUDA device (nerf_dbr_b200 has no CPU path)")
+        L.load_library()
+        self.config = config
+        if (config.get("hidden_dim", 256), config.get("position_encoding_levels", 10),
+                config.get("direction_encoding_levels", 4)) != (256, 10, 4):
+            raise ValueError("the B200 kernels implement the reference's 8x256 network with 10 / 4 encoding levels")
+        self.device = torch.device("cuda", int(config.get("device_index", torch.cuda.current_device())))
+        seed = config.get("seed")
+        if seed is not None:
+            torch.manual_seed(int(seed))
+        self.coarse_model = NeRFModel().to(self.device)
+        self.fine_model = NeRFModel().to(self.device)
+        params = list(self.coarse_model.parameters()) + list(self.fine_model.parameters())
+        self.optimizer = torch.optim.Adam(params, lr=config.get("lr", 5e-4), weight_decay=config.get("weight_decay", 0.0))
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(
+            self.optimizer, gamma=config.get("lr_decay", 0.1) ** (1 / config.get("decay_steps", 250000)))
+        self.n_coarse, self.n_fine = config.get("n_coarse", 64), config.get("n_fine", 128)
+        self.near, self.far = config.get("near", 2.0), config.get("far", 6.0)
+        self.gradient_clipping = config.get("gradient_clipping", None)
+        self.checkpoint_frequency = config.get("checkpoint_frequency", 50)
+        self.checkpoint_dir = config.get("checkpoint_dir", "checkpoints")
+        self.mode = {"bf16": L.BF16, "fp32": L.FP32}[config.get("precision", "bf16")]
+        self.step_fn = B200TrainStep(self.coarse_model, self.fine_model, self.n_coarse, self.n_fine, self.near, self.far,
+                                     mode=self.mode)
+        self.train_losses, self.val_losses = [], []
+        # ray selection and jitter: one generator, identical on every rank (each rank then takes its shard)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(seed) if seed is not None else 0)
+
+    # ------------------------------------------------------------------ one step (trainer.py:83-138)
+    def train_step(self, batch: Dict) -> float:
+        self.coarse_model.train()
+        self.fine_model.train()
+        image = batch["image"].to(self.device, torch.float32)
+        height, width = image.shape[:2]
+        rays_o, rays_d = ops.generate_rays(batch["pose"], width, height, float(batch["focal"]), device=self.device)
+        rays_o, rays_d, target = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), image.reshape(-1, 3)
+        n_rays = min(int(self.config.get("n_rays", 1024)), rays_o.shape[0])
+        select = torch.randperm(rays_o.shape[0], device=self.device, generator=self._gen)[:n_rays]
+        t_rand = torch.rand(n_rays, self.n_coarse, device=self.device, generator=self._gen)
+        rank, world = _dist()
+        first, count = ray_shard(rank, world, n_rays)
+        sel = select[first:first + count]
+        loss, _, _ = self.step_fn(rays_o[sel], rays_d[sel], target[sel], t_rand=t_rand[first:first + count].contiguous(),
+                                  n_rays_global=n_rays)
+        if self.gradient_clipping is not None:
+            torch.nn.utils.clip_grad_norm_(self.step_fn.parameters(), self.gradient_clipping)
+        self.optimizer.step()
+        self.scheduler.step()
+        return float(loss)
+
+    # ------------------------------------------------------------------ validation (trainer.py:140-170, 355-372)
+    def render_image(self, pose: torch.Tensor, img_shape, focal: float) -> torch.Tensor:
+        """The fine network's image, ``n_fine`` uniform samples per ray: what ``NeRFTrainer._render_image`` returns."""
+        height, width = img_shape
+        net = ops.pack_weights({k: v.detach() for k, v in self.fine_model.state_dict().items()}, self.device)
+        return ops.render_image(net, pose, width, height, self.n_fine, self.mode, float(focal), self.near, self.far)[0]
+
+    def validate(self, val_dataset) -> float:
+        self.coarse_model.eval()
+        self.fine_model.eval()
+        losses = []
+        with torch.no_grad():
+            for i in range(min(5, len(val_dataset))):
+                batch = val_dataset[i]
+                pred = self.render_image(batch["pose"], batch["image"].shape[:2], batch["focal"])
+                losses.append(float(torch.mean((pred - batch["image"].to(self.device, torch.float32)) ** 2)))
+        return float(sum(losses) / max(len(losses), 1))
+
+    # ------------------------------------------------------------------ epochs, checkpoints (trainer.py:172-268, 374-402)
+    def train(self, train_dataset, val_dataset=None, n_epochs: int = 100, verbose: bool = True) -> None:
+        say = print if verbose and _dist()[0] == 0 else (lambda *a, **k: None)
+        latest = self._find_latest_checkpoint()
+        if latest:
+            self.load_checkpoint(latest)
+            say(f"Resuming from {latest}: {len(self.train_losses)}/{n_epochs} epochs done")
+        start = len(self.train_losses)
+        for epoch in range(start, n_epochs):
+            losses = [self.train_step(train_dataset[i]) for i in range(len(train_dataset))]
+            self.train_losses.append(float(sum(losses) / max(len(losses), 1)))
+            if val_dataset is not None and (epoch + 1) % 10 == 0:
+                self.val_losses.append(self.validate(val_dataset))
+                say(f"Epoch {epoch + 1}: train {self.train_losses[-1]:.4f}, val {self.val_losses[-1]:.4f}")
+            else:
+                say(f"Epoch {epoch + 1}: train {self.train_losses[-1]:.4f}")
+            if (epoch + 1) % self.checkpoint_frequency == 0 and _dist()[0] == 0:
+                self.save_checkpoint(f"checkpoint_epoch_{epoch + 1}.pth")
+
+    def _find_latest_checkpoint(self) -> Optional[str]:
+        if not os.path.isdir(self.checkpoint_dir):
+            return None
+        best = None
+        for name in os.listdir(self.checkpoint_dir):
+            m = re.fullmatch(r"checkpoint_epoch_(\d+)\.pth", name)
+            if m and (best is None or int(m.group(1)) > best[0]):
+                best = (int(m.group(1)), os.path.join(self.checkpoint_dir, name))
+        return best[1] if best else None
+
+    def save_checkpoint(self, filename: str) -> str:
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        path = os.path.join(self.checkpoint_dir, filename)
+        save_checkpoint(path, self.step_fn, self.optimizer, self.scheduler, self.config, self.train_losses, self.val_losses)
+        return path
+
+    def load_checkpoint(self, path: str) -> None:
+        self.train_losses, self.val_losses = (list(x) for x in load_checkpoint(path, self.step_fn, self.optimizer, self.scheduler))
+
+    @staticmethod
+    def psnr(mse: float) -> float:
+        return float("inf") if mse <= 0 else -10.0 * math.log10(mse)
