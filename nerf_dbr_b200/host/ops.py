@@ -226,18 +226,29 @@ class TrainPass:
     workspace: passes whose phases overlap in time need different slots."""
 
     def __init__(self, model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_rays_global: Optional[int] = None,
-                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True, slot: int = 0, packed=None):
+                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True, slot: int = 0, packed=None,
+                 grad_out: Optional[dict] = None):
+        """``model``: an ``nn.Module`` with the reference's parameter names (gradients accumulate into ``p.grad``), or
+        a name -> tensor dict together with ``grad_out`` (name -> tensor the gradients accumulate into)."""
         self.lib = L.load_library()
         self.ro, self.rd, self.tg = (_dev(x, "train_fwd_bwd") for x in (rays_o, rays_d, target))
         self.n, self.n_samples, self.near, self.far, self.mode = self.ro.shape[0], n_samples, near, far, mode
         self.n_global = self.n if n_rays_global is None else n_rays_global
         dev = self.dev = self.ro.device
-        named = dict(model.named_parameters())
+        named = model if isinstance(model, dict) else dict(model.named_parameters())
+        if isinstance(model, dict) and grad_out is None:
+            raise ValueError("a parameter dict needs grad_out")
         params, grads = {}, {}
         for k in STATE_ORDER:
             p = named[k]
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise L.NerfB200Error("train_fwd_bwd", -101, f"parameter {k} must be a contiguous fp32 CUDA tensor")
+            if grad_out is not None:
+                gk = grad_out[k]
+                if not gk.is_cuda or gk.dtype != torch.float32 or not gk.is_contiguous() or gk.shape != p.shape:
+                    raise L.NerfB200Error("train_fwd_bwd", -101, f"grad_out[{k}] must be a contiguous fp32 CUDA tensor like the parameter")
+                params[k], grads[k] = p.detach(), gk
+                continue
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
             params[k], grads[k] = p.detach(), p.grad
