@@ -192,7 +192,8 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_rays, n_c, n_f = 4096, 64, 128
+    n_c, n_f = 64, 128
+    n_rays = 4096 * (world if args.weak else 1)     # global batch: configs[3] (strong), or configs[3] per GPU (weak)
     ck = O.seeded_checkpoint(5, 30.0)
     coarse, fine = nb.NeRFModel().to(dev), nb.NeRFModel().to(dev)
     coarse.load_state_dict(ck["coarse_model"]); fine.load_state_dict(ck["fine_model"])
@@ -207,7 +208,8 @@ def run_train(args):
     first, count = ray_shard(rank, world, n_rays)
     batches = []
     for i in range(args.steps + args.warmup):
-        sel = torch.randperm(200 * 150, generator=g)[:n_rays][first:first + count]
+        sel = (torch.randperm(200 * 150, generator=g)[:n_rays] if n_rays <= 200 * 150 else
+               torch.randint(0, 200 * 150, (n_rays,), generator=g))[first:first + count]
         batches.append((ro.reshape(-1, 3)[sel].to(dev), rd.reshape(-1, 3)[sel].to(dev), image.reshape(-1, 3)[sel].to(dev),
                         torch.rand(count, n_c, generator=g).to(dev)))
 
@@ -237,9 +239,10 @@ def run_train(args):
         flop = 3_095_808 * n_rays * (n_c + n_f)
         emit({"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+Adam", "value": n_rays / (ms * 1e-3),
               "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-              "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
               "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
               "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
+                         "global_rays": n_rays,
                          "loss_last": float(loss)},
               "gpu_launches": int(ops.launch_count() - n0),
               "roofline": train_roofline(args.precision, n_rays * (n_c + n_f), flop, ms)})
@@ -252,6 +255,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--overlap-sms", type=int, default=64, help="train workload: SMs given to the overlapped weight-gradient phase")
     ap.add_argument("--overlap", action="store_true", help="train workload: software-pipeline the passes (B200TrainStep overlap=True)")
+    ap.add_argument("--weak", action="store_true", help="train workload: 4096 rays per GPU instead of 4096 in total")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
