@@ -27,7 +27,6 @@
 namespace nerfb200 {
 
 constexpr int kChunkSamples = 524288;        // samples per chunk (multiple of 64): 9.5 GB of workspace at most
-constexpr int kWgradSplits = 148;            // tensor-core wgrad: one CTA per SM over the chunk's samples
 
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
                      float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, int sm_limit, cudaStream_t stream);

@@ -7,9 +7,11 @@
 // run of 8 KB blocks that is already the 128B-swizzled MN-major shared-memory image: one thread stages it with
 // two cp.async.bulk copies (A: rows_a/64 blocks, B: rows_b/64 blocks, three stages in flight -- the kernel is
 // HBM-bound) and the MMAs take both operands MN-major.  The fp32 accumulators of
-// the whole 256 x 256 tensor fill the 512 TMEM columns.  The slab range is split over CTAs; each writes its partial
-// to scratch and wgrad_reduce_kernel folds the partials into the caller's gradient tensor.  Bias gradients (row
-// sums of A) are taken from the staged tiles in shared memory by the otherwise idle epilogue warps.
+// the whole 256 x 256 tensor fill the 512 TMEM columns.  ONE launch covers every tensor of a chunk (a job table in the
+// kernel parameters; CTAs apportioned to jobs by operand bytes); a job's slab range is split over its CTAs, each
+// writes its partial to scratch and ONE wgrad_reduce_kernel launch folds the partials of all jobs into the caller's
+// gradient tensors.  Bias gradients (row sums of A) are taken from the staged tiles in shared memory by the
+// otherwise idle epilogue warps.
 //
 // reference: the autograd backward of the ten nn.Linear layers in NeRFModel (src/models/nerf.py:72-90)
 // inside NeRFTrainer.train_step (src/training/trainer.py:125-126).
