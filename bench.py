@@ -168,8 +168,13 @@ def train_roofline(precision, n_samples, flop, ms):
                 "frac": tfl / peaks()["bf16_tflops"], "traffic": None, "note": "FP32 CUDA-core kernels (gradient parity mode)"}
     bytes_per_sample = 4544 + 88 + 4352 + 88 + 9600 + 36
     gbs = bytes_per_sample * n_samples / (ms * 1e-3) / 1e9
+    traffic = None                                # measured DRAM bytes per 4096-ray step (ncu), when the batch is configs[3]
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and n_samples == 4096 * 192:
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("train_bf16_step_dram_bytes")
     return {"bound": "hbm", "achieved": gbs, "peak": peaks()["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks()["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes_per_sample": bytes_per_sample, "tflops": tfl,
+            "traffic": traffic, "algorithmic_bytes_per_sample": bytes_per_sample, "tflops": tfl,
             "tflops_frac_of_bf16_peak": tfl / peaks()["bf16_tflops"],
             "note": ("whole step: forward, dgrad chain and wgrad on tcgen05 (bf16 operands, fp32 accumulate); activations and "
                      "pre-activation gradients visit HBM once as bf16; write-only streams peak at 3.9 TB/s on this part")}
