@@ -157,7 +157,7 @@ def run_reference(args):
 
 
 def train_roofline(precision, n_samples, flop, ms):
-    """Step-level roofline of the training workload.  BF16 mode is HBM-bound by construction: the forward writes the
+    """Step-level roofline of the training workload, per GPU (n_samples, flop: this rank's share).  BF16 mode is HBM-bound by construction: the forward writes the
     bf16 operand blocks (4544 B/sample + 88 B of masks and head rows), the dgrad chain writes dpre (4352 B, reads
     88 B), the eleven wgrad launches read every operand once (9600 B), the ray kernel 36 B -- 18.7 KB per sample
     (DESIGN.md 4.3).  Pure-write streams top out at 3.9 TB/s on this part (tools/probe/hbm_write_bw.py), reads at
@@ -250,7 +250,7 @@ def run_train(args):
                          "global_rays": n_rays,
                          "loss_last": float(loss)},
               "gpu_launches": int(ops.launch_count() - n0),
-              "roofline": train_roofline(args.precision, n_rays * (n_c + n_f), flop, ms)})
+              "roofline": train_roofline(args.precision, n_rays * (n_c + n_f) // world, flop / world, ms)})      # per GPU
     if world > 1:
         dist.destroy_process_group()
 
