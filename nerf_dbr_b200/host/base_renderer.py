@@ -9,51 +9,67 @@ renderer.  This mirror is what runs standalone.
 """
 from __future__ import annotations
 
+import os
 import threading
 import time
 from abc import ABC, abstractmethod
 from contextlib import contextmanager
-from typing import Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
 from .model import NeRFModel
 
 
+# device -> (checkpoint path the pair was read from or None, coarse, fine); every SharedNeRFModel() is a
+# stateless view of this one table, which is what makes it "shared" between renderers
+_MODEL_CACHE: Dict[str, Tuple[Optional[str], NeRFModel, NeRFModel]] = {}
+
+
 class SharedNeRFModel:
-    """One (coarse, fine) model pair per device, loaded from a reference-format ``.pth``
-    (keys 'coarse_model' / 'fine_model', base_renderer.py:42-48).  Like the reference, a missing
-    checkpoint yields randomly initialised models (base_renderer.py:62-76)."""
+    """One (coarse, fine) model pair per device, read from a reference-format ``.pth`` (keys 'coarse_model' /
+    'fine_model', base_renderer.py:42-48).  Like the reference, a missing checkpoint file leaves the randomly
+    initialised pair in place and says so (base_renderer.py:62-76)."""
 
-    _instance = None
-    _models_by_device: dict = {}
-    _loaded_checkpoint = None
-
-    def __new__(cls):
-        if cls._instance is None:
-            cls._instance = super().__new__(cls)
-        return cls._instance
-
-    def load_models(self, checkpoint_path: str, device: str = "cpu"):
-        if device in self._models_by_device and self._loaded_checkpoint == checkpoint_path:
+    def load_models(self, checkpoint_path: str, device: str = "cpu") -> None:
+        cached = _MODEL_CACHE.get(device)
+        if cached is not None and cached[0] == checkpoint_path:
             return
-        coarse, fine = NeRFModel().to(device), NeRFModel().to(device)
-        try:
-            ckpt = torch.load(checkpoint_path, map_location=device, weights_only=False)
-            coarse.load_state_dict(ckpt["coarse_model"])
-            fine.load_state_dict(ckpt["fine_model"])
-            self._loaded_checkpoint = checkpoint_path
-        except FileNotFoundError:
-            print("Checkpoint not found, using randomly initialized models")
-        coarse.eval()
-        fine.eval()
-        self._models_by_device[device] = {"coarse": coarse, "fine": fine}
+        pair = [NeRFModel().to(device).eval() for _ in range(2)]        # coarse first, fine second
+        source: Optional[str] = None
+        if os.path.exists(checkpoint_path):
+            state = torch.load(checkpoint_path, map_location=device, weights_only=False)
+            for model, key in zip(pair, ("coarse_model", "fine_model")):
+                model.load_state_dict(state[key])
+            source = checkpoint_path
+        else:
+            print(f"checkpoint {checkpoint_path!r} does not exist: rendering with randomly initialised networks")
+        _MODEL_CACHE[device] = (source, pair[0], pair[1])
 
-    def get_models(self, device: str = "cpu"):
-        if device not in self._models_by_device:
-            raise RuntimeError(f"Models not loaded for device {device}. Call load_models() first.")
-        m = self._models_by_device[device]
-        return m["coarse"], m["fine"]
+    def get_models(self, device: str = "cpu") -> Tuple[NeRFModel, NeRFModel]:
+        if device not in _MODEL_CACHE:
+            raise RuntimeError(f"no models for device {device!r}: call load_models(checkpoint_path, device) first")
+        _, coarse, fine = _MODEL_CACHE[device]
+        return coarse, fine
+
+
+class _RssSampler(threading.Thread):
+    """Polls the process's resident set size every 10 ms until stopped; ``peak_mb`` is the largest value seen."""
+
+    def __init__(self):
+        super().__init__(daemon=True)
+        import psutil
+        self._proc, self._done = psutil.Process(), threading.Event()
+        self.peak_mb = self._proc.memory_info().rss / 2 ** 20
+
+    def run(self):
+        while not self._done.wait(0.01):
+            self.peak_mb = max(self.peak_mb, self._proc.memory_info().rss / 2 ** 20)
+
+    def finish(self) -> float:
+        self._done.set()
+        self.join()
+        return max(self.peak_mb, self._proc.memory_info().rss / 2 ** 20)
 
 
 class BaseUnifiedRenderer(ABC):
@@ -65,7 +81,6 @@ class BaseUnifiedRenderer(ABC):
         self.shared_model = SharedNeRFModel()
         self.last_render_time = 0.0
         self.peak_memory_mb = 0.0
-        self._monitoring = False
         self.near = 2.0
         self.far = 6.0
 
@@ -74,30 +89,21 @@ class BaseUnifiedRenderer(ABC):
 
     @contextmanager
     def performance_monitor(self):
-        """Wall time with device sync on both sides and peak host RSS, like the reference
-        (base_renderer.py:118-147)."""
-        import psutil
-        proc = psutil.Process()
-        self.peak_memory_mb = proc.memory_info().rss / 1024 / 1024
-        self._monitoring = True
-
-        def poll():
-            while self._monitoring:
-                self.peak_memory_mb = max(self.peak_memory_mb, proc.memory_info().rss / 1024 / 1024)
-                time.sleep(0.01)
-        th = threading.Thread(target=poll)
-        th.start()
-        if self.device.startswith("cuda"):
+        """Sets ``last_render_time`` (wall clock, device-synchronised on both sides) and ``peak_memory_mb`` (peak host
+        RSS) for the body, the two attributes the suite reads (base_renderer.py:118-147, benchmark_suite.py:207-208)."""
+        on_gpu = self.device.startswith("cuda")
+        sampler = _RssSampler()
+        sampler.start()
+        if on_gpu:
             torch.cuda.synchronize()
-        start = time.time()
+        t0 = time.perf_counter()
         try:
             yield
         finally:
-            if self.device.startswith("cuda"):
+            if on_gpu:
                 torch.cuda.synchronize()
-            self.last_render_time = time.time() - start
-            self._monitoring = False
-            th.join()
+            self.last_render_time = time.perf_counter() - t0
+            self.peak_memory_mb = sampler.finish()
 
     def get_device_info(self) -> str:
         if self.device.startswith("cuda"):
