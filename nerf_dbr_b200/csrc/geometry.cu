@@ -5,6 +5,7 @@
 // results (recipes: common.cuh, mirrored from oracle/scalar_oracle.c); writes are coalesced
 // and vectorised (one float4 store per thread for the 16 B/sample point stream).
 #include "common.cuh"
+#include <algorithm>
 
 namespace nerfb200 {
 
@@ -95,66 +96,89 @@ __global__ void sample_points_kernel(const float *__restrict__ rays_o,
 }
 
 // ------------------------------------------------------------------------------ importance
-// one warp per ray.  reference rendering.py:73-95 (+ shape fix); recipe SURVEY A5-A7:
+// reference rendering.py:73-95 (+ shape fix); recipe SURVEY A5-A7:
 //   total = torch.sum(w+1e-5): lane l accumulates elements l, l+32, ... ; lanes l, l+8, l+16,
 //   l+24 are combined ((a0+a1)+a2)+a3; the 8 results are added 0..7.
 //   cdf = running DOUBLE sum of fl(w/total), rounded to fp32 per element (serial: exact order).
-__global__ void importance_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+// A block of 8 warps works on `group` = 32 rays at a time (fewer when S is so large that 32 rows exceed shared memory):
+//   1. warp per ray (4 rays each): coalesced loads of w and z into shared memory, the exact-order total, and the
+//      quotients fl((w + 1e-5) / total) -- one division per lane and element, in parallel;
+//   2. THREAD per ray (warp 0, lane = ray): the serial double-precision running sum, 32 rays at once -- the order of
+//      additions inside a ray is what makes the cdf bit-exact, so the parallelism is across rays.  The rows have an
+//      odd pitch: 32 lanes walking 32 rows hit 32 different banks;
+//   3. warp per ray: inverse-CDF lookup (binary search, right = True), lerp, outputs.
+// The first version ran phase 2 on lane 0 of each ray's own warp: 2600 warp instructions per ray, 5 G per
+// 1600x1200 view, at 1/32 lane efficiency.
+__global__ void __launch_bounds__(256) importance_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
                                   const float *__restrict__ z_vals, const float *__restrict__ weights,
-                                  const float *__restrict__ u, int n_rays, int n_samples, int n_new,
+                                  const float *__restrict__ u, int n_rays, int n_samples, int n_new, int group,
                                   long long *__restrict__ indices, float *__restrict__ z_new,
                                   float *__restrict__ points)
 {
     extern __shared__ float smem[];
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *cdf = smem + (size_t)warp * (2 * n_samples + 2);   // [S+1]
-    float *zs = cdf + n_samples + 1;                          // [S]
-    for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
-        const float *w = weights + (size_t)ray * n_samples;
-        float part = 0.0f;
-        for (int s = lane; s < n_samples; s += 32) {
-            float v = __fadd_rn(__ldg(w + s), 1e-5f);
-            cdf[s + 1] = v;                                    // park w+1e-5
-            zs[s] = __ldg(z_vals + (size_t)ray * n_samples + s);
-            part = __fadd_rn(part, v);
-        }
-        float a1 = __shfl_sync(0xffffffffu, part, (lane & 7) + 8);
-        float a2 = __shfl_sync(0xffffffffu, part, (lane & 7) + 16);
-        float a3 = __shfl_sync(0xffffffffu, part, (lane & 7) + 24);
-        float a0 = __shfl_sync(0xffffffffu, part, (lane & 7));
-        float l8 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
-        float total = __shfl_sync(0xffffffffu, l8, 0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = 2 * n_samples + 3;                       // odd: [S+1] cdf, [S] z, 2 pad
+    for (int base = blockIdx.x * group; base < n_rays; base += gridDim.x * group) {     // group <= 32 rays per round
+        // ---- phase 1
+        for (int q = warp; q < group; q += 8) {
+            const int ray = base + q;
+            if (ray >= n_rays) continue;
+            float *cdf = smem + (size_t)q * pitch, *zs = cdf + n_samples + 1;
+            const float *w = weights + (size_t)ray * n_samples;
+            float part = 0.0f;
+            for (int s = lane; s < n_samples; s += 32) {
+                float v = __fadd_rn(__ldg(w + s), 1e-5f);
+                cdf[s + 1] = v;                                    // park w+1e-5
+                zs[s] = __ldg(z_vals + (size_t)ray * n_samples + s);
+                part = __fadd_rn(part, v);
+            }
+            float a1 = __shfl_sync(0xffffffffu, part, (lane & 7) + 8);
+            float a2 = __shfl_sync(0xffffffffu, part, (lane & 7) + 16);
+            float a3 = __shfl_sync(0xffffffffu, part, (lane & 7) + 24);
+            float a0 = __shfl_sync(0xffffffffu, part, (lane & 7));
+            float l8 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+            float total = __shfl_sync(0xffffffffu, l8, 0);
 #pragma unroll
-        for (int l = 1; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, l8, l));
-        __syncwarp();
-        if (lane == 0) {
+            for (int l = 1; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, l8, l));
+            for (int s = lane; s < n_samples; s += 32) cdf[s + 1] = __fdiv_rn(cdf[s + 1], total);
+        }
+        __syncthreads();
+        // ---- phase 2
+        if (warp == 0 && lane < group && base + lane < n_rays) {
+            float *cdf = smem + (size_t)lane * pitch;
             double run = 0.0;
             cdf[0] = 0.0f;
-            for (int s = 0; s < n_samples; ++s) {
-                run += (double)__fdiv_rn(cdf[s + 1], total);
-                cdf[s + 1] = (float)run;
+            for (int s = 1; s <= n_samples; ++s) {
+                run += (double)cdf[s];
+                cdf[s] = (float)run;
             }
         }
-        __syncwarp();
-        const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
-        const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
-        for (int k = lane; k < n_new; k += 32) {
-            size_t o = (size_t)ray * n_new + k;
-            float uk = __ldg(u + o);
-            int lo = 0, hi = n_samples + 1;                    // first index with cdf > u (right=True)
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= uk) lo = mid + 1; else hi = mid; }
-            int below = min(max(lo - 1, 0), n_samples - 1), above = min(lo, n_samples - 1);
-            float den = __fsub_rn(cdf[above], cdf[below]);
-            if (den < 1e-5f) den = 1.0f;
-            float t = __fdiv_rn(__fsub_rn(uk, cdf[below]), den);
-            float z = __fadd_rn(zs[below], __fmul_rn(t, __fsub_rn(zs[above], zs[below])));
-            indices[o] = lo;
-            z_new[o] = z;
-            points[3 * o + 0] = point_on_ray(ox, dx, z);
-            points[3 * o + 1] = point_on_ray(oy, dy, z);
-            points[3 * o + 2] = point_on_ray(oz, dz, z);
+        __syncthreads();
+        // ---- phase 3
+        for (int q = warp; q < group; q += 8) {
+            const int ray = base + q;
+            if (ray >= n_rays) continue;
+            const float *cdf = smem + (size_t)q * pitch, *zs = cdf + n_samples + 1;
+            const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
+            const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
+            for (int k = lane; k < n_new; k += 32) {
+                size_t o = (size_t)ray * n_new + k;
+                float uk = __ldg(u + o);
+                int lo = 0, hi = n_samples + 1;                    // first index with cdf > u (right=True)
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= uk) lo = mid + 1; else hi = mid; }
+                int below = min(max(lo - 1, 0), n_samples - 1), above = min(lo, n_samples - 1);
+                float den = __fsub_rn(cdf[above], cdf[below]);
+                if (den < 1e-5f) den = 1.0f;
+                float t = __fdiv_rn(__fsub_rn(uk, cdf[below]), den);
+                float z = __fadd_rn(zs[below], __fmul_rn(t, __fsub_rn(zs[above], zs[below])));
+                indices[o] = lo;
+                z_new[o] = z;
+                points[3 * o + 0] = point_on_ray(ox, dx, z);
+                points[3 * o + 1] = point_on_ray(oy, dy, z);
+                points[3 * o + 2] = point_on_ray(oz, dz, z);
+            }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -250,32 +274,43 @@ __global__ void composite_kernel(const float *__restrict__ sigma, const float *_
 // ------------------------------------------------------------------------------ merge
 // Sorted union of the coarse depths (ascending) and the importance samples (any order): the depths a
 // hierarchical fine pass renders (original-NeRF recipe; the reference leaves it undefined).  One warp per
-// ray; every element's output position is its rank, so the result equals torch.sort(cat(z, z_new)).values
-// bit for bit.
+// ray: the new samples are sorted in shared memory (bitonic network over the next power of two, +inf padding),
+// then every element's output position is its rank by one binary search in the other list -- a_i goes to
+// i + #{b < a_i}, sorted b_j to j + #{a <= b_j} -- so the result equals torch.sort(cat(z, z_new)).values bit for
+// bit.  O((na + nb) log) work per ray: the kernel is bound by its 8 (na + nb) bytes per ray of HBM traffic, not by
+// comparisons (the first version ranked every element by a linear scan: 13 G instructions at 1600x1200).
 __global__ void merge_samples_kernel(const float *__restrict__ z_a, const float *__restrict__ z_b, int n_rays, int na,
-                                     int nb, float *__restrict__ z_out)
+                                     int nb, int nb_pow2, float *__restrict__ z_out)
 {
     extern __shared__ float sm_merge[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *a = sm_merge + (size_t)warp * (na + nb), *b = a + na;
+    float *a = sm_merge + (size_t)warp * (na + nb_pow2), *b = a + na;
     for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
         for (int i = lane; i < na; i += 32) a[i] = __ldg(z_a + (size_t)ray * na + i);
-        for (int i = lane; i < nb; i += 32) b[i] = __ldg(z_b + (size_t)ray * nb + i);
+        for (int i = lane; i < nb_pow2; i += 32) b[i] = i < nb ? __ldg(z_b + (size_t)ray * nb + i) : __int_as_float(0x7f800000);
         __syncwarp();
+        for (int k = 2; k <= nb_pow2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (nb_pow2 >> 1); t += 32) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;     // the t-th pair at distance j
+                    const float x = b[lo], y = b[hi];
+                    const bool up = (lo & k) == 0;
+                    if ((x > y) == up) { b[lo] = y; b[hi] = x; }
+                }
+                __syncwarp();
+            }
         float *out = z_out + (size_t)ray * (na + nb);
-        for (int i = lane; i < na; i += 32) {              // a is sorted: rank = i + #{b < a_i}
-            float v = a[i];
-            int r = i;
-            for (int j = 0; j < nb; ++j) r += b[j] < v;
-            out[r] = v;
+        for (int i = lane; i < na; i += 32) {              // rank = i + #{b < a_i}
+            const float v = a[i];
+            int lo = 0, hi = nb;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (b[m] < v) lo = m + 1; else hi = m; }
+            out[i + lo] = v;
         }
-        for (int i = lane; i < nb; i += 32) {              // rank = #{a <= b_i} + #{b < b_i} + #{j < i : b_j == b_i}
-            float v = b[i];
+        for (int i = lane; i < nb; i += 32) {              // rank = i + #{a <= b_i}
+            const float v = b[i];
             int lo = 0, hi = na;
-            while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
-            int r = lo;
-            for (int j = 0; j < nb; ++j) r += (b[j] < v) || (b[j] == v && j < i);
-            out[r] = v;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
+            out[i + lo] = v;
         }
         __syncwarp();
     }
@@ -345,10 +380,16 @@ int nerf_b200_importance_sample(const float *rays_o, const float *rays_d, const 
         n_rays <= 0 || n_samples <= 0 || n_new <= 0)
         return NERF_B200_EINVAL;
     if (n_samples % 32 != 0 || n_samples > 1024) return NERF_B200_EUNSUPPORTED;
-    const int block = 128;
-    size_t smem = (size_t)(block / 32) * (2 * n_samples + 2) * sizeof(float);
-    importance_kernel<<<grid_for((size_t)n_rays * 32, block), block, smem, (cudaStream_t)stream>>>(
-        rays_o, rays_d, z_vals, weights, u, n_rays, n_samples, n_new, (long long *)indices, z_new, points);
+    const int block = 256;                                     // 8 warps share 32 rays per round
+    const int group = n_samples <= 384 ? 32 : n_samples <= 768 ? 16 : 8;
+    size_t smem = (size_t)group * (2 * n_samples + 3) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(importance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+    importance_kernel<<<grid_for(((size_t)n_rays + group - 1) / group * block, block, per_sm), block, smem, (cudaStream_t)stream>>>(
+        rays_o, rays_d, z_vals, weights, u, n_rays, n_samples, n_new, group, (long long *)indices, z_new, points);
     return launch_status();
 }
 
@@ -358,9 +399,15 @@ int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_ray
     if (!z_sorted || !z_new || !z_out || n_rays <= 0 || n_sorted <= 0 || n_new <= 0) return NERF_B200_EINVAL;
     if (n_sorted + n_new > 4096) return NERF_B200_EUNSUPPORTED;
     const int block = 128;
-    size_t smem = (size_t)(block / 32) * (n_sorted + n_new) * sizeof(float);
-    merge_samples_kernel<<<grid_for((size_t)n_rays * 32, block), block, smem, (cudaStream_t)stream>>>(
-        z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
+    int pow2 = 1;
+    while (pow2 < n_new) pow2 <<= 1;
+    size_t smem = (size_t)(block / 32) * (n_sorted + pow2) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    merge_samples_kernel<<<grid_for((size_t)n_rays * 32, block, 12), block, smem, (cudaStream_t)stream>>>(
+        z_sorted, z_new, n_rays, n_sorted, n_new, pow2, z_out);
     return launch_status();
 }
 
