@@ -181,3 +181,29 @@ def test_query_network_bf16_then_composite_equals_fused_render(S, checkpoints, p
     rgb_b, dep_b = ops.render_rays(net, ro, rd, S, mode=L.BF16)[:2]
     assert (rgb_a - rgb_b).abs().max().item() <= 2e-5
     assert (dep_a - dep_b).abs().max().item() <= 2e-4
+
+
+def test_render_rays_many_samples_per_ray(checkpoints, poses):
+    """Large S: 4096 samples per ray = 32 tiles per ray with the transmittance carried across tiles (BF16 and
+    BF16X3 against the oracle); the FP32 mode at its own limit of 2048 samples per ray; the documented limits above
+    (32768 on the tensor cores, 2048 in FP32 mode) return NERF_B200_EUNSUPPORTED."""
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host import lib as L
+    w = checkpoints["semi30"]["fine_model"]
+    net = packed_net(w)
+    ro, rd = O.camera_rays(poses["generic"], 6, 4)
+    ro, rd = ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3).contiguous()
+    with Watchdog() as wd:
+        for mode, S, tol in ((L.BF16, 4096, 3e-2), (L.BF16X3, 4096, 1e-4), (L.FP32, 2048, 1e-4)):
+            ref_rgb, ref_depth = O.render_rays(w, ro, rd, S)[:2]
+            rgb, dep = ops.render_rays(net, ro.cuda(), rd.cuda(), S, mode=mode)[:2]
+            torch.cuda.synchronize()
+            assert int(wd.word.item()) == 0
+            e = (rgb.cpu() - ref_rgb).abs().max().item()
+            print(f"S={S} mode {mode}: max|rgb| {e:.2e}, max|depth| {(dep.cpu() - ref_depth).abs().max().item():.2e}")
+            assert e <= tol, (mode, e)
+    for mode, S in ((L.BF16, 40000), (L.FP32, 2049)):
+        with pytest.raises(nb.NerfB200Error) as err:
+            ops.render_rays(net, ro.cuda(), rd.cuda(), S, mode=mode)
+        assert err.value.code == -2
