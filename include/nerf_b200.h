@@ -130,7 +130,10 @@ NERF_B200_API int nerf_b200_composite(const float *sigma, const float *rgb, cons
  * render_image: PyTorchCPURenderer.render_image (src/benchmark/pytorch_renderers.py:127-170):
  * ray generation, uniform sampling, positional encoding, the fine network and compositing in
  * ONE kernel; per-sample activations never reach HBM.  Renders rows [row0,row0+n_rows) of the
- * H x W image (the multi-GPU shard) -> rgb_out [n_rows*W,3], depth_out [n_rows*W]. */
+ * H x W image (the multi-GPU shard) -> rgb_out [n_rows*W,3], depth_out [n_rows*W].
+ * Limits: n_samples <= 32768 in the BF16 / BF16X3 modes (128-sample tiles, transmittance carried across the tiles
+ * of a ray), <= 2048 in FP32 mode; above: NERF_B200_EUNSUPPORTED.  n_samples == 1 renders black, as the reference
+ * does (its distance tensor is empty). */
 NERF_B200_API int nerf_b200_render_image(const void *packed, const float *c2w_host, int width, int height,
                            float focal, float near, float far, int n_samples, int row0,
                            int n_rows, int mode, float *rgb_out, float *depth_out, void *stream);
