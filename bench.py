@@ -190,7 +190,6 @@ def run_train(args):
     from nerf_dbr_b200.host import ops
     from nerf_dbr_b200.host.parallel import ray_shard
     from nerf_dbr_b200.host.trainer import B200TrainStep
-    from oracle import nerf_oracle as O
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -199,15 +198,14 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=dev)
     n_c, n_f = 64, 128
     n_rays = 4096 * (world if args.weak else 1)     # global batch: configs[3] (strong), or configs[3] per GPU (weak)
-    ck = O.seeded_checkpoint(5, 30.0)
-    coarse, fine = nb.NeRFModel().to(dev), nb.NeRFModel().to(dev)
-    coarse.load_state_dict(ck["coarse_model"]); fine.load_state_dict(ck["fine_model"])
+    from nerf_dbr_b200.host.synthetic import seeded_models
+    coarse, fine = seeded_models(5, 30.0, dev)           # seeded default init, density heads x30 (semi-opaque volume)
     from nerf_dbr_b200.host import lib as L
     step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32,
                          overlap=args.overlap, overlap_sms=args.overlap_sms)
     opt = torch.optim.Adam(step.parameters(), lr=5e-4, fused=True)      # the reference's optimizer, PyTorch's fused kernel
     pose = torch.eye(4); pose[2, 3] = 4.0
-    ro, rd = O.camera_rays(pose, 200, 150)
+    ro, rd = (t.cpu() for t in ops.generate_rays(pose, 200, 150, device=dev))
     g = torch.Generator().manual_seed(0)
     image = torch.rand(150, 200, 3, generator=g)
     first, count = ray_shard(rank, world, n_rays)
@@ -278,7 +276,7 @@ def main():
     import torch
     import torch.distributed as dist
     from nerf_dbr_b200.host import ops, lib as L
-    from oracle import nerf_oracle as O            # poses only (benchmark_pose restates generate_test_poses)
+    from nerf_dbr_b200.host.synthetic import orbit_pose
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,7 +297,7 @@ def main():
     rgb = torch.empty(n_rows, W, 3, device=dev)
     depth = torch.empty(n_rows, W, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    poses = [O.benchmark_pose(i % N_VIEWS, N_VIEWS) for i in range(args.steps + args.warmup)]
+    poses = [orbit_pose(i % N_VIEWS, N_VIEWS) for i in range(args.steps + args.warmup)]
 
     def step(i):
         ops.render_image(net, poses[i], W, H, S, mode, row0=row0, n_rows=n_rows, out_rgb=rgb, out_depth=depth)

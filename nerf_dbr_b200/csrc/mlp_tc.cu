@@ -29,7 +29,7 @@
 //   * The view direction enters colour layer 0 as an fp32 per-ray bias (W_dir . enc(d) + b),
 //     computed once per ray on CUDA cores: no per-sample direction encoding at all.
 //   * The density head rides in colour layer 0's GEMM as output column 128 (N = 144; bf16 like every
-//     other layer: < 0.01 dB against computing it in fp32, tools/emulate_bf16.py) instead of 256 CUDA-core
+//     other layer: < 0.01 dB against computing it in fp32, tests/diag/emulate_bf16.py) instead of 256 CUDA-core
 //     FMAs per sample.  Colour layer 0's epilogue -- relu(acc + per-ray bias) . W_c1 -> sigmoid, sigma =
 //     relu(col 128 + b) -- belongs to the back warps, which read the accumulator straight from TMEM and
 //     then composite (segmented warp scan of transmittance products); the epilogue warps go from layer 7

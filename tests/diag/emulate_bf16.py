@@ -3,7 +3,7 @@ operands, fp32 accumulation, fp32 per-ray direction bias, phase-shift positional
 Used to predict the kernel's error against the oracle before spending GPU time, and to localise
 a discrepancy (layout bug vs. numerics) when a GPU parity test fails.  Not part of the product."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import math
 import numpy as np
 import torch

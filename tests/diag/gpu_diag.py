@@ -1,7 +1,7 @@
 """First-contact GPU diagnostic: correctness numbers and rough timings for both precision modes,
 printed even when something is off (tests only say pass/fail).  Run under gpurun."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from nerf_dbr_b200.host import ops, lib as L

@@ -8,7 +8,7 @@ and |PSNR(bf16, T) - PSNR(reference, T)| <= 0.05 dB.  PSNR(bf16, reference) itse
 
 Fixtures: `lego` (trained-magnitude weights), `rand2`, `semi30`.  `trained11` (i.i.d. Gaussian
 weights at trained magnitudes) is an fp32-only fixture: such a network is chaotic in its
-high-frequency inputs -- tools/emulate_bf16.py shows ANY bf16 rounding of its activations moves
+high-frequency inputs -- tests/diag/emulate_bf16.py shows ANY bf16 rounding of its activations moves
 surfaces by whole samples -- which says nothing about a kernel."""
 import numpy as np
 import pytest

@@ -5,13 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from nerf_dbr_b200.host import ops
-from oracle import nerf_oracle as O
+from nerf_dbr_b200.host.synthetic import orbit_pose
 
 dev = torch.device("cuda", 0)
 z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
 net = ops.pack_weights({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev)
 W, H, NC, NI = 1600, 1200, 128, 128
-pose = O.benchmark_pose(1, 64)
+pose = orbit_pose(1, 64)
 ro, rd = ops.generate_rays(pose, W, H)
 ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
 u = torch.rand(ro.shape[0], NI, device=dev)

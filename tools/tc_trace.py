@@ -4,12 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from nerf_dbr_b200.host import ops, lib as L
-from oracle import nerf_oracle as O
+from nerf_dbr_b200.host.synthetic import orbit_pose
 
 dev = torch.device("cuda", 0)
 z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
 net = ops.pack_weights({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev)
-pose = O.benchmark_pose(1, 40)
+pose = orbit_pose(1, 40)
 TRAIN = len(sys.argv) > 1 and sys.argv[1] == "train"      # timeline of the TRAIN forward variant instead
 if TRAIN:
     import nerf_dbr_b200 as nb
