@@ -54,3 +54,48 @@ def test_full_size_properties(checkpoints, poses):
     rgb_s, dep_s = ops.composite(sigma.reshape(-1, S, 1), col.reshape(-1, S, 3), z, rd)[:2]
     assert (rgb_s.reshape(n, W, 3) - rgb[row0:row0 + n]).abs().max().item() <= 2e-5
     assert (dep_s.reshape(n, W) - dep[row0:row0 + n]).abs().max().item() <= 2e-4
+
+
+def test_full_size_training_step_properties():
+    """BASELINE.json configs[3]: 4096 rays, 64 coarse + 128 fine samples.  Properties that need no oracle:
+      * additivity (the data-parallel contract): the gradients and loss of the batch equal the accumulated gradients
+        and summed losses of its shards computed separately with the global ray count -- here 2 and 3 ragged shards;
+      * cross-mode agreement: the tensor-core mode against the FP32 CUDA-core mode, which small-size tests pin to the
+        reference's autograd (loss within 0.5 %, every gradient tensor within 15 %: the mode's bf16 precision)."""
+    from nerf_dbr_b200.host import lib as L
+    from nerf_dbr_b200.host.synthetic import seeded_models
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    n = 4096
+    g = torch.Generator().manual_seed(11)
+    ro = (torch.zeros(n, 3) + torch.tensor([0.0, 0.0, 4.0])).cuda()
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, -1.0]), dim=-1).cuda()
+    tgt, tr = torch.rand(n, 3, generator=g).cuda(), torch.rand(n, 64, generator=g).cuda()
+
+    def run(mode, shards):
+        coarse, fine = seeded_models(5, 30.0, "cuda")
+        step = B200TrainStep(coarse, fine, 64, 128, mode=mode)
+        total, acc, first = 0.0, None, 0
+        for count in shards:
+            sl = slice(first, first + count)
+            loss, _, _ = step(ro[sl], rd[sl], tgt[sl], t_rand=tr[sl].contiguous(), n_rays_global=n)   # zeroes, then accumulates
+            grads = [p.grad.double().clone() for p in step.parameters()]
+            acc = grads if acc is None else [a + b for a, b in zip(acc, grads)]
+            total += float(loss)
+            first += count
+        return total, acc, [k for m in (coarse, fine) for k, _ in m.named_parameters()]
+
+    with Watchdog() as wd:
+        l1, g1, names = run(L.BF16, [n])
+        l2, g2, _ = run(L.BF16, [2048, 2048])
+        l3, g3, _ = run(L.BF16, [1000, 2000, 1096])
+        l32, g32, _ = run(L.FP32, [n])
+        torch.cuda.synchronize()
+        assert int(wd.word.item()) == 0
+    for lx, gx in ((l2, g2), (l3, g3)):
+        assert abs(lx - l1) <= 1e-5 * l1
+        worst = max(float((a - b).norm()) / max(float(a.norm()), 1e-30) for a, b in zip(g1, gx))
+        assert worst <= 1e-3, worst
+    rel = sorted(((float((a - b).norm()) / max(float(b.norm()), 1e-30), k) for a, b, k in zip(g1, g32, names)), reverse=True)
+    print(f"4096 rays: loss bf16 {l1:.6f} fp32 {l32:.6f}; worst gradient tensors bf16 vs fp32:", [(f"{e:.1e}", k) for e, k in rel[:3]])
+    assert abs(l1 - l32) <= 5e-3 * l32
+    assert rel[0][0] <= 0.15, rel[0]
