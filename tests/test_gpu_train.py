@@ -274,6 +274,34 @@ def test_split_phase_pipeline_equals_back_to_back(checkpoints, poses):
         assert float((a - b).norm()) <= 1e-4 * max(float(a.norm()), 1e-20)
 
 
+def test_flat_gradient_bucket_survives_zero_grad_to_none(checkpoints, poses):
+    """B200TrainStep keeps all 44 gradients as views of one flat buffer (one memset, in-place all-reduce).  The
+    reference's loop calls ``optimizer.zero_grad()`` (set_to_none=True by default), which drops the views: the next
+    step must re-attach them and produce the same gradients as a fresh object."""
+    from nerf_dbr_b200.host import lib as L
+    from nerf_dbr_b200.host.trainer import B200TrainStep
+    ck = O.seeded_checkpoint(5, 30.0)
+    ro, rd = O.camera_rays(poses["generic"], 16, 8)
+    ro, rd = ro.reshape(-1, 3).contiguous().cuda(), rd.reshape(-1, 3).contiguous().cuda()
+    g = torch.Generator().manual_seed(2)
+    tgt, tr = torch.rand(128, 3, generator=g).cuda(), torch.rand(128, 64, generator=g).cuda()
+    coarse, fine = models_from(ck)
+    step = B200TrainStep(coarse, fine, 64, 128, mode=L.FP32)
+    opt = torch.optim.Adam(step.parameters(), lr=0.0)          # lr 0: the weights stay put, the protocol is exercised
+    step(ro, rd, tgt, t_rand=tr)
+    flat = step._flat
+    assert all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in step.parameters())
+    first = [p.grad.clone() for p in step.parameters()]
+    opt.step()
+    opt.zero_grad()                                            # grads -> None
+    assert all(p.grad is None for p in step.parameters())
+    step(ro, rd, tgt, t_rand=tr)
+    assert step._flat is flat
+    for a, p in zip(first, step.parameters()):
+        assert p.grad.data_ptr() >= flat.data_ptr()
+        assert float((p.grad - a).norm()) <= 1e-5 * max(float(a.norm()), 1e-20)
+
+
 def test_checkpoint_round_trip_reference_format(tmp_path, checkpoints, poses):
     """A checkpoint written after CUDA training steps has the reference's keys (trainer.py:374-388), loads through the
     renderer's SharedNeRFModel path (base_renderer.py:42-48) and resumes training bit-identically."""
