@@ -56,12 +56,22 @@ __device__ void fill_operands(uint8_t *sm, uint32_t tm, uint32_t b_bytes)
     fence_proxy_async_smem();
 }
 
-__global__ void __launch_bounds__(128, 1) solo_kernel(int reps, long long *cycles)
+// STREAM > 0: warp 1 additionally pulls `STREAM` KB stages from a 1 MiB L2-resident buffer into shared memory with
+// cp.async.bulk, back to back through a 4-slot ring (the fused kernel streams 1 MiB of weights per tile per SM, about
+// 57 B/clk; unthrottled this probe pulls more) -- what does the L2 -> shared-memory weight stream cost in clocks?
+template <int STREAM>
+__global__ void __launch_bounds__(128, 1) solo_kernel_t(int reps, long long *cycles, const unsigned char *wbuf, unsigned long long *streamed)
 {
     extern __shared__ uint8_t raw[];
     uint8_t *sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
     const uint32_t base = smem_u32(sm), bar = base + kBarOff, tptr = base + kTptrOff;
-    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    volatile int *stop = reinterpret_cast<volatile int *>(sm + kTptrOff + 16);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar + 8 + 8 * i, 1);
+        *stop = 0;
+        fence_mbar_init();
+    }
     if (threadIdx.x < 32) tmem_alloc<512>(tptr);
     tc_fence_before_sync();
     __syncthreads();
@@ -83,6 +93,30 @@ __global__ void __launch_bounds__(128, 1) solo_kernel(int reps, long long *cycle
         mma_commit(bar);
         wait_or_trap(bar);
         if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+        *stop = 1;
+    } else if (STREAM > 0 && threadIdx.x == 32) {
+        // ring of 4 slots behind the operands (smem offset 72 KB..), each STREAM KB
+        unsigned long long n = 0;
+        uint32_t phase[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i) {
+            mbar_arrive_expect_tx(bar + 8 + 8 * i, STREAM * 1024);
+            bulk_g2s(base + 72 * 1024 + i * STREAM * 1024, wbuf + ((n * STREAM * 1024) & ((1u << 20) - 1)), STREAM * 1024, bar + 8 + 8 * i);
+            ++n;
+        }
+        while (!*stop) {
+            const int i = (int)(n & 3);
+            const long long t1 = clock64();
+            while (!mbar_try_wait(bar + 8 + 8 * i, phase[i])) if (clock64() - t1 > 2000000000LL) __trap();
+            phase[i] ^= 1;
+            mbar_arrive_expect_tx(bar + 8 + 8 * i, STREAM * 1024);
+            bulk_g2s(base + 72 * 1024 + i * STREAM * 1024, wbuf + ((n * STREAM * 1024) & ((1u << 20) - 1)), STREAM * 1024, bar + 8 + 8 * i);
+            ++n;
+        }
+        for (int i = 0; i < 4; ++i) {                        // drain
+            const long long t1 = clock64();
+            while (!mbar_try_wait(bar + 8 + 8 * i, phase[i])) if (clock64() - t1 > 2000000000LL) __trap();
+        }
+        if (blockIdx.x == 0) streamed[0] = n * STREAM * 1024;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -139,6 +173,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pair_kernel(
     }
 }
 
+template <int STREAM>
+static void run_solo(const char *name, int reps, double flop, long long *d, const unsigned char *wbuf, unsigned long long *streamed)
+{
+    const int smem = (72 + 4 * (STREAM > 0 ? STREAM : 1) + 2) * 1024;
+    cudaFuncSetAttribute(solo_kernel_t<STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int pass = 0; pass < 3; ++pass) {
+        cudaMemset(streamed, 0, 8);
+        cudaEventRecord(e0);
+        solo_kernel_t<STREAM><<<148, 128, smem>>>(reps, d, wbuf, streamed);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("%s: error %s\n", name, cudaGetErrorString(e)); exit(1); }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+        unsigned long long bytes; cudaMemcpy(&bytes, streamed, 8, cudaMemcpyDeviceToHost);
+        if (pass) printf("%-9s grid 148 reps %8d | %8.2f ms | %7.1f TFLOP/s | %5.0f MHz | L2->smem stream %5.1f B/clk/SM (%.2f TB/s total)\n", name, reps, ms,
+                         flop * reps * 148 / (ms * 1e-3) / 1e12, cyc / (ms * 1e3), (double)bytes / cyc, bytes * 148.0 / (ms * 1e-3) / 1e12);
+    }
+}
+
 template <typename K>
 static void run(const char *name, K kernel, int grid, int reps, double flop_per_cta_rep, long long *d)
 {
@@ -163,9 +219,18 @@ int main(int argc, char **argv)
     long long *d; cudaMalloc(&d, 16);
     const int reps = argc > 1 ? atoi(argv[1]) : 700000;      // 11.2 M MMAs per issuer: ~0.5 s
     const double flop = 16.0 * 2.0 * 128 * 128 * 16;          // per CTA and repetition (the pair issuer covers two CTAs)
-    run("solo", solo_kernel, 148, reps, flop, d);
+    unsigned char *wbuf; cudaMalloc(&wbuf, 1 << 20); cudaMemset(wbuf, 0x3c, 1 << 20);
+    unsigned long long *streamed; cudaMalloc(&streamed, 8);
+    if (argc > 2) {                                           // L2 -> shared-memory weight-stream experiment
+        run_solo<0>("solo", reps, flop, d, wbuf, streamed);
+        run_solo<8>("solo+8KB", reps, flop, d, wbuf, streamed);
+        run_solo<32>("solo+32KB", reps, flop, d, wbuf, streamed);
+        run_solo<0>("solo", reps, flop, d, wbuf, streamed);
+        return 0;
+    }
+    run_solo<0>("solo", reps, flop, d, wbuf, streamed);
     run("pair", pair_kernel, 148, reps, flop, d);
-    run("solo", solo_kernel, 148, reps, flop, d);
+    run_solo<0>("solo", reps, flop, d, wbuf, streamed);
     run("pair", pair_kernel, 148, reps, flop, d);
     return 0;
 }
