@@ -124,6 +124,8 @@ struct Args {
     float *ws;                 // TRAIN: training workspace [R_TOTAL][ws_ch] (train_layout.h); rays are chunk-local
     int ws_ch;
     unsigned int *dbg;         // optional: [0] = first timeout code
+    int pair;                  // cluster size 1, 2 or 4: the CTAs of a cluster share the weight stream -- each loads 1/size of
+                               // every stage and multicasts it to all of them (1/size of the L2 -> shared-memory reads per SM)
     int sm_limit;              // 0 = every SM; else at most this many CTAs (the caller runs something else beside)
     long long *trace;          // optional timeline (tools/tc_trace.py): CTA 0, first kTraceTiles tiles
 };
@@ -657,6 +659,7 @@ struct IssueCtx {
     uint64_t pedesc;        // smem descriptor of this tile's encoded-position operand (hi plane)
     uint32_t pe_empty_bar;  // barrier released when layer 4 has consumed the encoded position
     int tile;               // CTA-local tile index
+    uint16_t pair_mask;     // != 0: weight ring shared with the peer CTAs of the cluster: release slots in all of them
     unsigned int *dbg;
     long long *trace;       // this tile's trace rows or nullptr
 };
@@ -712,7 +715,10 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &x)
             mma_commit(x.bars + 8u * (c.layer == 8 ? B_ACCC0 : B_ACCFULL + c.half));
             if (x.trace) x.trace[c.layer * 8 + (last_of_layer ? 2 : 1)] = clock64();
         }
-        if constexpr (CI % kStageChunks == kStageChunks - 1) mma_commit(x.bars + 8u * (B_WEMPTY + slot));
+        if constexpr (CI % kStageChunks == kStageChunks - 1) {
+            if (x.pair_mask) mma_commit_mcast(x.bars + 8u * (B_WEMPTY + slot), x.pair_mask);
+            else mma_commit(x.bars + 8u * (B_WEMPTY + slot));
+        }
         if constexpr (c.layer == 4 && last_of_layer) mma_commit(x.pe_empty_bar);
     }
     __syncwarp();
@@ -742,11 +748,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
 
     const int tile_begin = blockIdx.x * a.tiles_per_cta;
     const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_cta);
-    const int my_tiles = max(0, tile_end - tile_begin);
+    // paired CTAs consume the shared weight stream in lockstep: both run tiles_per_cta tiles, the ones past the end
+    // of the work are ghosts (every row invalid, nothing written)
+    const bool pair = a.pair > 1;
+    const int my_tiles = pair ? a.tiles_per_cta : max(0, tile_end - tile_begin);
+    const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;           // 0 .. a.pair - 1
 
     // ---- one-time setup -------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::kWSlots; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+        for (int i = 0; i < C::kWSlots; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), pair ? a.pair : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PEFULL + i), 4); mbar_init(bar(B_PEEMPTY + i), 1);
         }
@@ -770,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (pair) cluster_sync_all();                          // the peer's barriers exist before anything is multicast at them
     tc_fence_after_sync();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + SM_TMEM);
 
@@ -784,6 +795,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     if (round > 0) wait_bar(bar(B_WEMPTY + slot), (round - 1) & 1, a.dbg, 1);
                     const uint32_t bytes = stage_bytes(st), dst = sm_base + SM_W + slot * C::kSlotBytes;
                     mbar_arrive_expect_tx(bar(B_WFULL + slot), SPLIT ? 2 * bytes : bytes);
+                    if (pair) {
+                        // this CTA fetches its 1/size piece of the stage for every CTA of the cluster; the other pieces
+                        // arrive from the peers.  A slot is refilled only after ALL MMA issuers released it (B_WEMPTY
+                        // counts one arrival per CTA), so no copy can overtake a reader.
+                        const uint32_t piece = bytes / (uint32_t)a.pair, off = cta_rank * piece;
+                        const uint16_t mask = (uint16_t)((1u << a.pair) - 1u);
+                        bulk_g2s_mcast(dst + off, wb + stage_offset(st) + off, piece, bar(B_WFULL + slot), mask);
+                        if (SPLIT) bulk_g2s_mcast(dst + kStageSlotBytes + off, wb_lo + stage_offset(st) + off, piece, bar(B_WFULL + slot), mask);
+                        continue;
+                    }
                     bulk_g2s(dst, wb + stage_offset(st), bytes, bar(B_WFULL + slot));
                     if (SPLIT) bulk_g2s(dst + kStageSlotBytes, wb_lo + stage_offset(st), bytes, bar(B_WFULL + slot));
                 }
@@ -794,6 +815,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         // warp-uniform control flow; one elected lane issues the tcgen05 instructions
         IssueCtx x;
         x.bars = bars;
+        x.pair_mask = pair ? (uint16_t)((1u << a.pair) - 1u) : (uint16_t)0;
         x.wdesc = smem_desc_sw128(sm_base + SM_W);
         x.dbg = a.dbg;
         for (int t = 0; t < my_tiles; ++t) {
@@ -884,6 +906,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before_sync();
     __syncthreads();
+    if (pair) cluster_sync_all();                          // no CTA leaves while its peer may still signal into it
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc<512>(tmem_base);
@@ -917,16 +940,42 @@ static int plan(Args &a)
     int per = (a.n_tiles + sms - 1) / sms;
     per = ((per + a.tiles_per_ray - 1) / a.tiles_per_ray) * a.tiles_per_ray;   // a ray never straddles CTAs
     a.tiles_per_cta = per;
-    return (a.n_tiles + per - 1) / per;               // grid
+    int grid = (a.n_tiles + per - 1) / per;
+    if (a.pair > 1) grid = (grid + a.pair - 1) / a.pair * a.pair;   // whole clusters (trailing CTAs may run ghost tiles only)
+    return grid;
+}
+
+// Cluster size of the shared weight stream: 2 unless NERF_B200_CLUSTER=1|2|4 in the environment says otherwise (A/B
+// measurements; 1 = every CTA streams all the weights itself).  Measured at 800x600x128 on B200: 2 = +1.6..2.1 %
+// (SM clock 1522 -> 1552 MHz under the power cap); 4 = 0.62x, because 37 clusters of four one-CTA-per-SM blocks do
+// not all fit the GPCs at once and the launch runs in two waves.
+static int cluster_default()
+{
+    const char *e = getenv("NERF_B200_CLUSTER");
+    const int v = e ? atoi(e) : 2;
+    return (v == 1 || v == 2 || v == 4) ? v : 2;
 }
 
 template <int SRC, bool SPLIT, bool TRAIN = false>
 static int launch(Args &a, cudaStream_t stream)
 {
+    a.pair = TRAIN ? 1 : cluster_default();           // the TRAIN variant is bound by its HBM writes: pairing buys nothing there
     int grid = plan(a);
+    if (a.pair > 1 && a.n_tiles < 4 * grid) { a.pair = 1; grid = plan(a); }  // small launches: ghost tiles would dominate
     if (grid < 0) return grid;
     cudaError_t e = cudaFuncSetAttribute(fused_render_kernel<SRC, SPLIT, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    if (a.pair > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = a.pair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, fused_render_kernel<SRC, SPLIT, TRAIN>, a);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+        return launch_status();
+    }
     fused_render_kernel<SRC, SPLIT, TRAIN><<<grid, kThreads, kSmemBytes, stream>>>(a);
     return launch_status();
 }
