@@ -201,8 +201,7 @@ def run_train(args):
     from nerf_dbr_b200.host.synthetic import seeded_models
     coarse, fine = seeded_models(5, 30.0, dev)           # seeded default init, density heads x30 (semi-opaque volume)
     from nerf_dbr_b200.host import lib as L
-    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32,
-                         overlap=args.overlap, overlap_sms=args.overlap_sms)
+    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32)
     opt = torch.optim.Adam(step.parameters(), lr=5e-4, fused=True)      # the reference's optimizer, PyTorch's fused kernel
     pose = torch.eye(4); pose[2, 3] = 4.0
     ro, rd = (t.cpu() for t in ops.generate_rays(pose, 200, 150, device=dev))
@@ -256,8 +255,6 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--overlap-sms", type=int, default=64, help="train workload: SMs given to the overlapped weight-gradient phase")
-    ap.add_argument("--overlap", action="store_true", help="train workload: software-pipeline the passes (B200TrainStep overlap=True)")
     ap.add_argument("--weak", action="store_true", help="train workload: 4096 rays per GPU instead of 4096 in total")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)

@@ -23,23 +23,14 @@ class B200TrainStep:
     """Replaces NeRFTrainer._render_rays + loss + backward.  Data parallel: every rank passes its
     shard of the ray batch and the GLOBAL ray count; gradients are all-reduce-summed over NCCL.
 
-    ``overlap=True`` (BF16 mode, large batch) runs the step as a software pipeline over three passes (coarse
-    network, two halves of the fine network's rays): a pass's activation phase (forward, compositing backward, dgrad
-    chain) is bound by HBM *writes* (3.9 TB/s on B200), its weight-gradient phase by HBM *reads*, so pass i's
-    activation phase runs on most SMs while pass i-1's weight gradients stream on the remaining ``overlap_sms`` on a
-    second stream.  Gradients accumulate, so the result is the same sum over rays.  Measured on B200 (4096 rays,
-    64 + 128 samples): 4.30-4.80 ms per step for 64..32 weight-gradient SMs against 4.20 ms back to back -- the
-    activation phases are SM-bound (epilogue issue) as well as write-bound, so they slow down by what the
-    weight gradients gain.  Hence off by default; kept because the split-phase entry point is what a caller needs to
-    overlap the coarse network's gradient all-reduce with the fine network's compute."""
+    (A software-pipelined schedule over the split-phase entry point -- one pass's weight gradients on a second stream
+    and a few SMs beside the next pass's activation phase -- was measured at 4.30-4.80 ms per step against 4.20 ms back
+    to back and removed; ``ops.TrainPass`` keeps the split phases for callers that want to overlap a collective.)"""
 
     def __init__(self, coarse: NeRFModel, fine: NeRFModel, n_coarse: int = 64, n_fine: int = 128,
-                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32, overlap: bool = False, overlap_sms: int = 64):
+                 near: float = 2.0, far: float = 6.0, mode: int = L.FP32):
         self.coarse, self.fine = coarse, fine
         self.n_coarse, self.n_fine, self.near, self.far, self.mode = n_coarse, n_fine, near, far, mode
-        self.overlap, self.overlap_sms = overlap, overlap_sms
-        self._side = None
-        self._live = None
         self._flat = None                            # one bucket: every gradient is a view of it, + 1 slot for the loss
 
     def _attach_flat_grads(self):
@@ -63,16 +54,6 @@ class B200TrainStep:
     def parameters(self):
         return list(self.coarse.parameters()) + list(self.fine.parameters())
 
-    # samples per pass below which the pipeline's extra launches cost more than the overlap hides
-    MIN_PIPELINE_SAMPLES = 131072
-    MAX_PASS_SAMPLES = 524288                  # one workspace chunk (nerf_b200_train_fwd_bwd_ex split phases)
-
-    def _pipelined(self, n_rays: int) -> bool:
-        half = n_rays // 2
-        return (self.overlap and self.mode == L.BF16 and n_rays >= 2 and
-                min(n_rays * self.n_coarse, half * self.n_fine) >= self.MIN_PIPELINE_SAMPLES and
-                max(n_rays * self.n_coarse, (n_rays - half) * self.n_fine) <= self.MAX_PASS_SAMPLES)
-
     def __call__(self, rays_o, rays_d, target, t_rand: Optional[torch.Tensor] = None,
                  n_rays_global: Optional[int] = None, allreduce: bool = True):
         """Zeroes the gradients, runs forward+backward of both networks, all-reduces when a process
@@ -88,12 +69,9 @@ class B200TrainStep:
             t_rand = torch.rand(rays_o.shape[0], self.n_coarse, device=rays_o.device)
         n = rays_o.shape[0]
         kw = dict(n_rays_global=n if n_rays_global is None else n_rays_global, near=self.near, far=self.far, mode=self.mode)
-        if not self._pipelined(n):
-            lc, rgb_c = ops.train_fwd_bwd(self.coarse, rays_o, rays_d, target, self.n_coarse, t_rand, **kw)
-            lf, rgb_f = ops.train_fwd_bwd(self.fine, rays_o, rays_d, target, self.n_fine, None, **kw)
-            loss = lc + lf
-        else:
-            loss, rgb_c, rgb_f = self._pipeline(rays_o, rays_d, target, t_rand, kw)
+        lc, rgb_c = ops.train_fwd_bwd(self.coarse, rays_o, rays_d, target, self.n_coarse, t_rand, **kw)
+        lf, rgb_f = ops.train_fwd_bwd(self.fine, rays_o, rays_d, target, self.n_fine, None, **kw)
+        loss = lc + lf
         if allreduce and _world_size() > 1:
             if flat is not None:                     # in place on the bucket (4.24 MB over NVLink); the loss rides in its last slot
                 flat[-1] = loss
@@ -102,36 +80,6 @@ class B200TrainStep:
             else:
                 loss = allreduce_sum_([p.grad for p in self.parameters()], extra=loss)
         return loss, rgb_c, rgb_f
-
-    def _pipeline(self, rays_o, rays_d, target, t_rand, kw):
-        dev = rays_o.device
-        main = torch.cuda.current_stream(dev)
-        if self._side is None:
-            self._side = torch.cuda.Stream(dev)
-        side = self._side
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        w_sms = max(1, min(self.overlap_sms, sms - 1))
-        h = rays_o.shape[0] // 2
-        pc = ops.TrainPass(self.coarse, rays_o, rays_d, target, self.n_coarse, t_rand, slot=0, **kw)
-        pf1 = ops.TrainPass(self.fine, rays_o[:h], rays_d[:h], target[:h], self.n_fine, None, slot=1, **kw)
-        pf2 = ops.TrainPass(self.fine, rays_o[h:], rays_d[h:], target[h:], self.n_fine, None, slot=0, packed=pf1.packed, **kw)
-        passes = [pc, pf1, pf2]
-        done = [None] * len(passes)                  # side-stream events: weight gradients of pass i finished
-        passes[0].run(L.TRAIN_ACTIVATIONS)
-        for i in range(1, len(passes)):
-            ready = main.record_event()              # activations of pass i-1 are complete
-            if i >= 2:
-                main.wait_event(done[i - 2])         # pass i reuses the workspace slot of pass i-2
-            passes[i].run(L.TRAIN_ACTIVATIONS, sm_limit=sms - w_sms)     # enqueued first: its CTAs claim their SMs
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                passes[i - 1].run(L.TRAIN_WEIGHT_GRADS, sm_limit=w_sms)
-                done[i - 1] = side.record_event()
-        main.wait_event(done[-2])
-        passes[-1].run(L.TRAIN_WEIGHT_GRADS)
-        self._live = passes                          # keep buffers referenced until the next step re-creates them
-        loss = pc.loss + pf1.loss + pf2.loss
-        return loss, pc.rgb, torch.cat([pf1.rgb, pf2.rgb], dim=0)
 
 
 def save_checkpoint(path: str, step: B200TrainStep, optimizer, scheduler=None, config=None, train_losses=(),

@@ -245,33 +245,41 @@ def test_train_bf16_mode_ragged_shapes(n_rays, S, jitter, checkpoints, poses):
         assert float((p.grad - 2 * first[name]).norm()) <= 1e-3 * max(float(first[name].norm()), 1e-20), name
 
 
-def test_split_phase_pipeline_equals_back_to_back(checkpoints, poses):
-    """nerf_b200_train_fwd_bwd_ex: activation and weight-gradient phases as separate calls on two streams with SM
-    limits (B200TrainStep overlap=True: coarse, fine half 1, fine half 2) accumulate the same gradients and loss as
-    the back-to-back step, up to the order of fp32 atomic additions."""
-    from nerf_dbr_b200.host import lib as L
-    from nerf_dbr_b200.host.trainer import B200TrainStep
+def test_split_phases_equal_single_call(checkpoints, poses):
+    """nerf_b200_train_fwd_bwd_ex: the activation phase and the weight-gradient phase as two calls (with an SM limit on
+    each) accumulate the same gradients, loss and colours as the single call, up to the order of fp32 atomic
+    additions; split phases are refused where they cannot work (FP32 mode)."""
+    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import lib as L, ops
     ck = O.seeded_checkpoint(11, 30.0)
-    n = 2048                                               # 131072 coarse samples, 2 x 131072 fine samples
-    ro, rd = O.camera_rays(poses["generic"], 64, 32)
+    n = 1024
+    ro, rd = O.camera_rays(poses["generic"], 64, 16)
     ro, rd = ro.reshape(-1, 3).contiguous().cuda(), rd.reshape(-1, 3).contiguous().cuda()
     g = torch.Generator().manual_seed(3)
     tgt, tr = torch.rand(n, 3, generator=g).cuda(), torch.rand(n, 64, generator=g).cuda()
     out = []
     with Watchdog() as wd:
-        for overlap in (False, True):
-            coarse, fine = models_from(ck)
-            step = B200TrainStep(coarse, fine, 64, 128, mode=L.BF16, overlap=overlap, overlap_sms=40)
-            assert step._pipelined(n) == overlap
-            loss, rgb_c, rgb_f = step(ro, rd, tgt, t_rand=tr)
+        for split in (False, True):
+            coarse, _ = models_from(ck)
+            tp = ops.TrainPass(coarse, ro, rd, tgt, 64, tr, mode=L.BF16)
+            if split:
+                tp.run(L.TRAIN_ACTIVATIONS, sm_limit=100)
+                torch.cuda.synchronize()                      # the phases may be arbitrarily far apart in time
+                tp.run(L.TRAIN_WEIGHT_GRADS, sm_limit=48)
+            else:
+                tp.run()
             torch.cuda.synchronize()
             assert int(wd.word.item()) == 0
-            out.append((float(loss), rgb_c.cpu(), rgb_f.cpu(), [p.grad.cpu().double() for p in step.parameters()]))
-    (l0, c0, f0, g0), (l1, c1, f1, g1) = out
+            out.append((float(tp.loss), tp.rgb.cpu(), [p.grad.cpu().double() for p in coarse.parameters()]))
+    (l0, c0, g0), (l1, c1, g1) = out
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
-    assert torch.equal(c0, c1) and torch.equal(f0, f1)
+    assert torch.equal(c0, c1)
     for a, b in zip(g0, g1):
         assert float((a - b).norm()) <= 1e-4 * max(float(a.norm()), 1e-20)
+    coarse, _ = models_from(ck)
+    with pytest.raises(nb.NerfB200Error) as e:
+        ops.TrainPass(coarse, ro, rd, tgt, 64, tr, mode=L.FP32).run(L.TRAIN_ACTIVATIONS)
+    assert e.value.code == -2
 
 
 def test_flat_gradient_bucket_survives_zero_grad_to_none(checkpoints, poses):
