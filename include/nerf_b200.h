@@ -193,6 +193,9 @@ NERF_B200_API int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200
                                int mode, void *workspace, float *loss_sum, float *rgb_out,
                                int phases, int sm_limit, void *stream);
 
+/* Environment (read at every tensor-core render launch, for A/B measurements only): NERF_B200_CLUSTER=1 makes every
+ * CTA stream the whole weight set itself instead of sharing the stream inside 2-CTA clusters (the default, 2). */
+
 /* ---- introspection (tests / bench) -------------------------------------------------------
  * Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 NERF_B200_API uint64_t nerf_b200_launch_count(void);
