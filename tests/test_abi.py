@@ -39,7 +39,8 @@ def test_sass_is_blackwell_native():
         pytest.skip("cuobjdump not on PATH")
     L.build_library()
     sass = subprocess.run(["cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+    # tcgen05 MMA, TMEM loads, bulk (TMA-engine) copies, and the cluster forms of the paired weight stream
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UBLKCP.S.G.MULTICAST", "UTCBAR.MULTICAST", "UCGABAR_ARV"):
         assert mnemonic in sass, mnemonic
     assert "HMMA." not in sass.replace("UTCHMMA", "")      # no legacy mma.sync path
 
