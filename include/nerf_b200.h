@@ -10,9 +10,12 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
  *     parameter name ends in _host;  all tensors are dense row-major fp32 unless stated.
- *   - the caller owns every buffer (inputs, outputs, packed weights); nothing here
- *     calls cudaMalloc/cudaFree, nothing keeps state between calls -> re-entrant
- *     across streams and devices.
+ *   - the caller owns every buffer (inputs, outputs, packed weights, workspaces); nothing here
+ *     calls cudaMalloc/cudaFree and no data survives a call -> re-entrant across streams and
+ *     devices.  One exception: train_fwd_bwd in BF16 mode creates two auxiliary streams and three
+ *     events per device on first use and reuses them (its weight-gradient launches fork onto them
+ *     and join back into the caller's stream before the call returns), so training calls for ONE
+ *     device must come from one host thread at a time.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *     all work is enqueued asynchronously on it.
  *   - return value: 0 = ok, negative = NERF_B200_E* argument error (nothing was
