@@ -12,7 +12,8 @@
  *     parameter name ends in _host;  all tensors are dense row-major fp32 unless stated.
  *   - the caller owns every buffer (inputs, outputs, packed weights, workspaces); nothing here
  *     calls cudaMalloc/cudaFree and no data survives a call -> re-entrant across streams and
- *     devices.  One exception: train_fwd_bwd in BF16 mode creates two auxiliary streams and three
+ *     devices (the launch counter is atomic, the two debug hooks at the end of this header are per
+ *     device).  One exception: train_fwd_bwd in BF16 mode creates two auxiliary streams and three
  *     events per device on first use and reuses them (its weight-gradient launches fork onto them
  *     and join back into the caller's stream before the call returns), so training calls for ONE
  *     device must come from one host thread at a time.
@@ -196,18 +197,23 @@ NERF_B200_API int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200
                                int mode, void *workspace, float *loss_sum, float *rgb_out,
                                int phases, int sm_limit, void *stream);
 
-/* Environment (read at every tensor-core render launch, for A/B measurements only): NERF_B200_CLUSTER=1 makes every
- * CTA stream the whole weight set itself instead of sharing the stream inside 2-CTA clusters (the default, 2). */
+/* Environment (read ONCE per process, at the first tensor-core render launch; for A/B measurements only):
+ * NERF_B200_CLUSTER=1 makes every CTA stream the whole weight set itself instead of sharing the stream inside 2-CTA
+ * clusters (the default, 2). */
 
 /* ---- introspection (tests / bench) -------------------------------------------------------
  * Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 NERF_B200_API uint64_t nerf_b200_launch_count(void);
-/* Optional watchdog word (device, 4 bytes, zero it first; NULL to detach).  The tensor-core kernel's
- * barrier waits are bounded: on a timeout the kernel stores 0x80000000 | code<<16 | block here and
- * traps (the launch then fails with a CUDA error instead of hanging the device). */
+/* Optional watchdog word (device, 4 bytes, zero it first), kept PER DEVICE: the word is filed under the device that
+ * owns the pointer and only handed to launches on that device; NULL detaches the current device's word.  While a word
+ * is attached the tensor-core kernels' barrier waits are bounded (~2 s of SM clocks): on a timeout the kernel stores
+ * tag | code<<16 | block here (tag 0x8 render/forward, 0x9 dgrad chain, 0xA wgrad) and traps, so a protocol bug fails
+ * the launch instead of hanging the device.  With no word attached (production) a wait never traps -- preemption,
+ * a debugger or throttled clocks may stretch it -- it backs off with nanosleep and keeps waiting. */
 NERF_B200_API void nerf_b200_set_watchdog_word(unsigned int *device_word);
 /* Optional timeline buffer (device, 6*9*8 int64, zeroed): CTA 0 of render_image(BF16) stores clock64
- * stamps of its MMA issuer and one epilogue warp for its first 6 tiles (tools/tc_trace.py). NULL detaches. */
+ * stamps of its MMA issuer and one epilogue warp for its first 6 tiles (tools/tc_trace.py).  Per device like the
+ * watchdog word; NULL detaches the current device's buffer. */
 NERF_B200_API void nerf_b200_set_trace_buffer(long long *device_buf);
 
 #ifdef __cplusplus

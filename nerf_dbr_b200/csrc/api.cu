@@ -11,13 +11,47 @@ int tc_query_points(const void *, const float *, const float *, long long, float
 }
 using namespace nerfb200;
 
-namespace nerfb200 { extern long long *g_tc_trace; }
-static unsigned int *g_watchdog = nullptr;
+// Debug hooks are kept PER DEVICE: a word allocated on cuda:0 is never handed to a kernel on cuda:1.  A pointer is
+// filed under the device that owns it (cudaPointerGetAttributes); NULL detaches the current device's hook.
+namespace nerfb200 {
+constexpr int kMaxDevices = 64;
+static std::atomic<unsigned int *> g_watchdog[kMaxDevices];
+static std::atomic<long long *> g_trace[kMaxDevices];
+static int device_of(const void *p)
+{
+    int dev = 0;
+    if (p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) return at.device;
+        cudaGetLastError();
+    }
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return dev;
+}
+unsigned int *watchdog_word()
+{
+    const int d = device_of(nullptr);
+    return d >= 0 && d < kMaxDevices ? g_watchdog[d].load(std::memory_order_acquire) : nullptr;
+}
+long long *trace_buffer()
+{
+    const int d = device_of(nullptr);
+    return d >= 0 && d < kMaxDevices ? g_trace[d].load(std::memory_order_acquire) : nullptr;
+}
+}  // namespace nerfb200
 
 extern "C" {
 
-void nerf_b200_set_watchdog_word(unsigned int *device_word) { g_watchdog = device_word; }
-void nerf_b200_set_trace_buffer(long long *device_buf) { nerfb200::g_tc_trace = device_buf; }
+void nerf_b200_set_watchdog_word(unsigned int *device_word)
+{
+    const int d = device_of(device_word);
+    if (d >= 0 && d < kMaxDevices) g_watchdog[d].store(device_word, std::memory_order_release);
+}
+void nerf_b200_set_trace_buffer(long long *device_buf)
+{
+    const int d = device_of(device_buf);
+    if (d >= 0 && d < kMaxDevices) g_trace[d].store(device_buf, std::memory_order_release);
+}
 
 int nerf_b200_query_network(const void *packed, const float *positions, const float *directions,
                             int64_t n, int mode, float *sigma, float *rgb, void *stream)
@@ -27,7 +61,7 @@ int nerf_b200_query_network(const void *packed, const float *positions, const fl
     if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
     // BF16: the fused tensor-core kernel with a (point, direction) pair per row; the direction part of colour layer 0
     // is an fp32 per-row bias built by the back warps
-    if (mode == NERF_B200_BF16) return tc_query_points(packed, positions, directions, n, sigma, rgb, g_watchdog, (cudaStream_t)stream);
+    if (mode == NERF_B200_BF16) return tc_query_points(packed, positions, directions, n, sigma, rgb, watchdog_word(), (cudaStream_t)stream);
     return NERF_B200_EUNSUPPORTED;
 }
 
@@ -44,7 +78,7 @@ int nerf_b200_render_image(const void *packed, const float *c2w_host, int width,
                                 rgb_out, depth_out, (cudaStream_t)stream);
     if (mode == NERF_B200_BF16 || mode == NERF_B200_BF16X3)
         return tc_render_pose(packed, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows,
-                              mode == NERF_B200_BF16X3, rgb_out, depth_out, g_watchdog, (cudaStream_t)stream);
+                              mode == NERF_B200_BF16X3, rgb_out, depth_out, watchdog_word(), (cudaStream_t)stream);
     return NERF_B200_EINVAL;
 }
 
@@ -60,7 +94,7 @@ int nerf_b200_render_rays_ex(const void *packed, const float *rays_o, const floa
                                 depth_out, acc_out, weights_out, (cudaStream_t)stream);
     if (mode == NERF_B200_BF16 || mode == NERF_B200_BF16X3)
         return tc_render_rays(packed, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, z_vals,
-                              mode == NERF_B200_BF16X3, rgb_out, depth_out, acc_out, weights_out, g_watchdog,
+                              mode == NERF_B200_BF16X3, rgb_out, depth_out, acc_out, weights_out, watchdog_word(),
                               (cudaStream_t)stream);
     return NERF_B200_EINVAL;
 }

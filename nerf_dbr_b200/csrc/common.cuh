@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
 
 #include "../../include/nerf_b200.h"
 #include "packed_layout.h"
@@ -10,10 +11,13 @@
 namespace nerfb200 {
 
 // launch accounting (nerf_b200_launch_count)
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
+// per-device debug hooks (api.cu): the watchdog word / timeline buffer registered for the CURRENT device, or nullptr
+unsigned int *watchdog_word();
+long long *trace_buffer();
 inline int launch_status()
 {
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     return 0;

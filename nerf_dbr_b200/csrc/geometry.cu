@@ -9,7 +9,7 @@
 
 namespace nerfb200 {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 // ------------------------------------------------------------------------------ rays
 // one thread per output float: e -> (ray, component).  reference base_renderer.py:223-258
@@ -340,7 +340,7 @@ extern "C" {
 
 int nerf_b200_abi_version(void) { return NERF_B200_ABI_VERSION; }
 
-uint64_t nerf_b200_launch_count(void) { return g_launches; }
+uint64_t nerf_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char *nerf_b200_error_string(int code)
 {

@@ -135,18 +135,9 @@ constexpr int kTraceTiles = 6;
 //   3 EPI(warp 4): half 0 acc_full seen   4 EPI: half 0 a_ready arrive   5 EPI: layer done
 //   6 EPI: last half acc_full seen
 
-constexpr long long kTimeoutCycles = 4000000000LL;
-
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, unsigned int *dbg, uint32_t code)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kTimeoutCycles) {
-            if (dbg) atomicCAS(dbg, 0u, 0x80000000u | (code << 16) | (blockIdx.x & 0xffffu));
-            __trap();
-        }
-    }
+    mbar_wait_bounded(bar, parity, dbg, 0x80000000u, code);
 }
 
 struct RowInfo { int ray, s; bool valid; };
@@ -951,9 +942,12 @@ static int plan(Args &a)
 // not all fit the GPCs at once and the launch runs in two waves.
 static int cluster_default()
 {
-    const char *e = getenv("NERF_B200_CLUSTER");
-    const int v = e ? atoi(e) : 2;
-    return (v == 1 || v == 2 || v == 4) ? v : 2;
+    static const int v = [] {                         // read once per process (documented in include/nerf_b200.h)
+        const char *e = getenv("NERF_B200_CLUSTER");
+        const int x = e ? atoi(e) : 2;
+        return (x == 1 || x == 2 || x == 4) ? x : 2;
+    }();
+    return v;
 }
 
 template <int SRC, bool SPLIT, bool TRAIN = false>
@@ -982,14 +976,13 @@ static int launch(Args &a, cudaStream_t stream)
 
 }  // namespace tc
 
-long long *g_tc_trace = nullptr;     // set through nerf_b200_set_trace_buffer (tools/tc_trace.py)
 
 int tc_render_pose(const void *packed, const float *c2w, int width, int height, float focal, float near,
                    float far, int n_samples, int row0, int n_rows, bool split, float *rgb_out, float *depth_out,
                    unsigned int *dbg, cudaStream_t stream)
 {
     tc::Args a = {};
-    a.trace = g_tc_trace;
+    a.trace = trace_buffer();
     a.packed = reinterpret_cast<const unsigned char *>(packed);
     a.pose = pose_from_c2w(c2w);
     a.width = width; a.row0 = row0;
@@ -1039,7 +1032,7 @@ int tc_train_forward(const void *packed, const float *rays_o, const float *rays_
     a.n_rays = n_rays; a.n_samples = n_samples;
     a.near = near; a.far = far;
     a.ws = ws; a.ws_ch = ws_ch; a.dbg = dbg;
-    a.trace = g_tc_trace;
+    a.trace = trace_buffer();
     return tc::launch<tc::SRC_RAYS, false, true>(a, stream);
 }
 

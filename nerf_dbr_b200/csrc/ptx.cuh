@@ -50,6 +50,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Bounded parity wait shared by the tensor-core kernels.  With a watchdog word attached (nerf_b200_set_watchdog_word:
+// tests, debugging) a wait that exceeds ~2 s of SM clocks records `tag | code << 16 | block` in the word and traps, so
+// a barrier-protocol bug fails the launch instead of hanging the device.  Without one (production) the wait never
+// traps: time-slicing, MPS preemption, a debugger or a throttled clock may legitimately stretch it -- after the same
+// bound it backs off with nanosleep and keeps waiting.
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity, unsigned int *dbg, uint32_t tag, uint32_t code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    bool slow = false;
+    while (!mbar_try_wait(bar, parity)) {
+        if (slow) { __nanosleep(256); continue; }
+        if (clock64() - t0 > 4000000000LL) {
+            if (dbg) {
+                atomicCAS(dbg, 0u, tag | (code << 16) | (blockIdx.x & 0xffffu));
+                __trap();
+            }
+            slow = true;
+        }
+    }
+}
 // remote (cluster) arrive on the barrier at the same offset in CTA `cta`
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)
 {

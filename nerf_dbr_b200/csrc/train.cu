@@ -461,11 +461,13 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
             // forward on the tensor cores (TRAIN variant of the fused kernel); pad columns of the stored
             // activations must be finite zeros: wgrad multiplies them by zero gradients
             const int n_smp = a.n_rays * n_samples;
-            if (a.ch != n_smp)                          // the last slab of the bf16 operand rows (activations and dpre)
-                cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)G_TOTAL * 128, stream);
+            if (a.ch != n_smp) {                        // the last slab of the bf16 operand rows (activations and dpre)
+                cudaError_t me = cudaMemsetAsync(reinterpret_cast<__nv_bfloat16 *>(a.ws) + big_tile(0, a.ch / 64 - 1), 0, (size_t)G_TOTAL * 128, stream);
+                if (me != cudaSuccess) { cudaGetLastError(); return (int)me; }
+            }
             const float *tr = t_rand ? t_rand + (size_t)r0 * n_samples : nullptr;
             if ((rc = tc_train_forward(packed, rays_o + 3 * (size_t)r0, rays_d + 3 * (size_t)r0, a.n_rays, n_samples, near, far,
-                                       tr, a.ws, a.ch, nullptr, sm_limit, stream)))
+                                       tr, a.ws, a.ch, watchdog_word(), sm_limit, stream)))
                 return rc;
         } else {
             train_fwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
@@ -477,10 +479,11 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
             // dgrad chain on the tensor cores; the pad columns of the dpre rows are zero since the memset above
             const int n_smp = a.n_rays * n_samples;
             if (a.ch != n_smp) {
-                cudaMemset2DAsync(a.ws + (size_t)R_DSIG * a.ch + n_smp, (size_t)a.ch * sizeof(float), 0,
-                                  (size_t)(a.ch - n_smp) * sizeof(float), 4, stream);       // dsig, dy (fp32 rows)
+                cudaError_t me = cudaMemset2DAsync(a.ws + (size_t)R_DSIG * a.ch + n_smp, (size_t)a.ch * sizeof(float), 0,
+                                                   (size_t)(a.ch - n_smp) * sizeof(float), 4, stream);       // dsig, dy (fp32 rows)
+                if (me != cudaSuccess) { cudaGetLastError(); return (int)me; }
             }
-            if ((rc = dgrad_chain_tc(packed, a.ws, a.ch, n_smp, nullptr, sm_limit, stream))) return rc;
+            if ((rc = dgrad_chain_tc(packed, a.ws, a.ch, n_smp, watchdog_word(), sm_limit, stream))) return rc;
         } else {
             train_bwd_kernel<<<std::min(tiles, sms), kSimtThreads, sizeof(SimtSmem), stream>>>(a);
             if ((rc = launch_status())) return rc;
@@ -521,25 +524,41 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
                                                    const_cast<float *>(db));
             return launch_status();
         };
-        if ((rc = wgrad(row(R_DPRE), 256, row(R_PE), 63, g.layer_w[0], 63, 0, g.layer_b[0]))) return rc;
-        for (int l = 1; l < 8; ++l) {
-            const int ld = l == 4 ? 319 : 256;
-            if ((rc = wgrad(row(R_DPRE + 256 * l), 256, row(R_H + 256 * (l - 1)), 256, g.layer_w[l], ld, 0, g.layer_b[l]))) return rc;
-            if (l == 4 && (rc = wgrad(row(R_DPRE + 256 * 4), 256, row(R_PE), 63, g.layer_w[4], 319, 256, nullptr))) return rc;
-        }
-        if ((rc = wgrad(row(R_DSIG), 1, row(R_H + 256 * 7), 256, g.density_w, 256, 0, g.density_b))) return rc;
-        if ((rc = wgrad(row(R_DPREC0), 128, row(R_H + 256 * 7), 256, g.color0_w, 283, 0, g.color0_b))) return rc;
-        if ((rc = wgrad(row(R_DPREC0), 128, row(R_DE), 27, g.color0_w, 283, 256, nullptr))) return rc;
-        if ((rc = wgrad(row(R_DY), 3, row(R_C0H), 128, g.color1_w, 128, 0, g.color1_b))) return rc;
-        if (tc) {
-            if ((rc = wgrad_tc_batch(reinterpret_cast<const __nv_bfloat16 *>(ws), (int)ch, jobs, n_jobs, scratch,
-                                     sm_limit > 0 ? std::min(sms, sm_limit) : sms, wst->s[0])))
-                return rc;
-            for (int i = 0; i < 2; ++i)                 // join: the caller's stream continues after both
-                if ((ce = cudaEventRecord(wst->join[i], wst->s[i])) != cudaSuccess ||
-                    (ce = cudaStreamWaitEvent(stream, wst->join[i], 0)) != cudaSuccess)
-                    return (int)ce;
-        }
+        // the auxiliary streams are joined back into the caller's stream on EVERY path out of here, error or not:
+        // an unjoined fork would leave later work on `stream` unordered against launches already queued on them
+        bool forked = tc;
+        auto join = [&]() -> int {
+            if (!forked) return 0;
+            forked = false;
+            int bad = 0;
+            for (int i = 0; i < 2; ++i) {
+                cudaError_t je = cudaEventRecord(wst->join[i], wst->s[i]);
+                if (je == cudaSuccess) je = cudaStreamWaitEvent(stream, wst->join[i], 0);
+                if (je != cudaSuccess && !bad) { cudaGetLastError(); bad = (int)je; }
+            }
+            return bad;
+        };
+        auto all_wgrads = [&]() -> int {
+            int rc2;
+            if ((rc2 = wgrad(row(R_DPRE), 256, row(R_PE), 63, g.layer_w[0], 63, 0, g.layer_b[0]))) return rc2;
+            for (int l = 1; l < 8; ++l) {
+                const int ld = l == 4 ? 319 : 256;
+                if ((rc2 = wgrad(row(R_DPRE + 256 * l), 256, row(R_H + 256 * (l - 1)), 256, g.layer_w[l], ld, 0, g.layer_b[l]))) return rc2;
+                if (l == 4 && (rc2 = wgrad(row(R_DPRE + 256 * 4), 256, row(R_PE), 63, g.layer_w[4], 319, 256, nullptr))) return rc2;
+            }
+            if ((rc2 = wgrad(row(R_DSIG), 1, row(R_H + 256 * 7), 256, g.density_w, 256, 0, g.density_b))) return rc2;
+            if ((rc2 = wgrad(row(R_DPREC0), 128, row(R_H + 256 * 7), 256, g.color0_w, 283, 0, g.color0_b))) return rc2;
+            if ((rc2 = wgrad(row(R_DPREC0), 128, row(R_DE), 27, g.color0_w, 283, 256, nullptr))) return rc2;
+            if ((rc2 = wgrad(row(R_DY), 3, row(R_C0H), 128, g.color1_w, 128, 0, g.color1_b))) return rc2;
+            if (tc)
+                return wgrad_tc_batch(reinterpret_cast<const __nv_bfloat16 *>(ws), (int)ch, jobs, n_jobs, scratch,
+                                      sm_limit > 0 ? std::min(sms, sm_limit) : sms, wst->s[0]);
+            return 0;
+        };
+        rc = all_wgrads();
+        const int jrc = join();
+        if (rc) return rc;
+        if (jrc) return jrc;
     }
     return 0;
 }

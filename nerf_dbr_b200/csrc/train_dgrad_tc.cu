@@ -52,14 +52,7 @@ struct Args {
 
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, unsigned int *dbg, uint32_t code)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            if (dbg) atomicCAS(dbg, 0u, 0x90000000u | (code << 16) | (blockIdx.x & 0xffffu));
-            __trap();
-        }
-    }
+    mbar_wait_bounded(bar, parity, dbg, 0x90000000u, code);
 }
 
 struct IssueCtx { uint32_t bars; uint32_t region[2]; uint64_t wdesc; unsigned int *dbg; };

@@ -52,6 +52,7 @@ struct Args {
     int n_slabs;                                 // samples / 64
     int n_jobs;
     int cta_begin[kMaxJobs + 1];
+    unsigned int *dbg;                           // optional watchdog word (ptx.cuh: mbar_wait_bounded)
     Job job[kMaxJobs];
 };
 struct ReduceArgs {                              // block b reduces 64 elements of job j, blk_begin[j] <= b < blk_begin[j + 1]
@@ -62,13 +63,6 @@ struct ReduceArgs {                              // block b reduces 64 elements 
     float *dW[kMaxJobs];
     int ld[kMaxJobs], col_off[kMaxJobs];
 };
-
-__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
-{
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > 4000000000LL) __trap();
-}
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ Args args)
 {
@@ -81,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const uint32_t sm_base = smem_u32(sm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) { return sm_base + SM_BAR + 8u * i; };
+    auto wait = [&](uint32_t b, uint32_t parity) { mbar_wait_bounded(b, parity, args.dbg, 0xA0000000u, 0u); };
     const int per = (args.n_slabs + splits - 1) / splits;
     const int c_begin = split * per, c_end = min(args.n_slabs, c_begin + per);
     const int my_slabs = max(0, c_end - c_begin);
@@ -286,6 +281,7 @@ int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_
     wg::Args a = {};
     wg::ReduceArgs r = {};
     a.ws = ws; a.n_slabs = ch / 64; a.n_jobs = r.n_jobs = n_jobs;
+    a.dbg = watchdog_word();
     ctas = std::max(ctas, n_jobs);
     int weight[wg::kMaxJobs], share[wg::kMaxJobs], total_w = 0, given = 0;
     for (int j = 0; j < n_jobs; ++j) {

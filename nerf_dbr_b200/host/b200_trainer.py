@@ -18,7 +18,7 @@ import torch
 from . import lib as L
 from . import ops
 from .model import NeRFModel
-from .parallel import ray_shard
+from .parallel import broadcast_parameters_, ray_shard
 from .trainer import B200TrainStep, load_checkpoint, save_checkpoint
 
 
@@ -33,7 +33,7 @@ class B200Trainer:
     """Mirror of ``NeRFTrainer`` (trainer.py:18-81).  ``config`` keys read: hidden_dim / position_encoding_levels /
     direction_encoding_levels (must be the reference's 256 / 10 / 4: the kernels are specialised for that network),
     lr, weight_decay, lr_decay, decay_steps, n_coarse, n_fine, n_rays, near, far, gradient_clipping,
-    checkpoint_frequency, plus ``precision`` ('bf16' | 'fp32'), ``device_index``, ``seed``,
+    checkpoint_frequency, plus ``precision`` ('bf16' | 'fp32'), ``device_index`` (default: ``$LOCAL_RANK``, else the current device), ``seed``,
     ``checkpoint_dir`` (default 'checkpoints', as the reference)."""
 
     def __init__(self, config: Dict):
@@ -44,13 +44,18 @@ class B200Trainer:
         if (config.get("hidden_dim", 256), config.get("position_encoding_levels", 10),
                 config.get("direction_encoding_levels", 4)) != (256, 10, 4):
             raise ValueError("the B200 kernels implement the reference's 8x256 network with 10 / 4 encoding levels")
-        self.device = torch.device("cuda", int(config.get("device_index", torch.cuda.current_device())))
+        # one process per GPU under torchrun: LOCAL_RANK picks the device unless the config names one
+        default_index = int(os.environ.get("LOCAL_RANK", torch.cuda.current_device()))
+        self.device = torch.device("cuda", int(config.get("device_index", default_index)))
         seed = config.get("seed")
         if seed is not None:
             torch.manual_seed(int(seed))
         self.coarse_model = NeRFModel().to(self.device)
         self.fine_model = NeRFModel().to(self.device)
         params = list(self.coarse_model.parameters()) + list(self.fine_model.parameters())
+        # data parallel: every replica starts from rank 0's weights (an unseeded config would otherwise give every rank
+        # its own random initialisation, and the all-reduced gradients would belong to no single model)
+        broadcast_parameters_(params)
         self.optimizer = torch.optim.Adam(params, lr=config.get("lr", 5e-4), weight_decay=config.get("weight_decay", 0.0))
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(
             self.optimizer, gamma=config.get("lr_decay", 0.1) ** (1 / config.get("decay_steps", 250000)))
@@ -144,6 +149,7 @@ class B200Trainer:
 
     def load_checkpoint(self, path: str) -> None:
         self.train_losses, self.val_losses = (list(x) for x in load_checkpoint(path, self.step_fn, self.optimizer, self.scheduler))
+        broadcast_parameters_(self.step_fn.parameters())       # replicas restart identical even if only rank 0's file is current
 
     @staticmethod
     def psnr(mse: float) -> float:

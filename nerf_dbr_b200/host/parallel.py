@@ -44,6 +44,21 @@ def allreduce_sum_(tensors: Iterable[torch.Tensor], extra: Optional[torch.Tensor
     return flat[off:].reshape(extra.shape) if extra is not None else None
 
 
+def broadcast_parameters_(tensors: Iterable[torch.Tensor], src: int = 0, group=None) -> None:
+    """Make every rank's replicas equal to rank ``src``'s, in place, as ONE flat broadcast (data-parallel training: the
+    replicas must start -- and restart after a checkpoint load -- from identical weights, or the summed gradients belong
+    to no single model).  No-op without an initialised process group or with world size 1."""
+    tensors = [t.data if isinstance(t, torch.nn.Parameter) else t for t in tensors]
+    if not tensors or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in tensors])
+    dist.broadcast(flat, src=src, group=group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
 def gather_rows(band: torch.Tensor, height: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Optional: assemble the full image on ``dst`` from every rank's band (rows may differ by one, so the
     bands are padded to the largest).  Not on the timed path."""

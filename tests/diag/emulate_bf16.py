@@ -60,8 +60,8 @@ def render_image(w, pose, W_, H_, S):
 
 
 if __name__ == "__main__":
-    g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "golden_render.npz"))
-    z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ckpt_lego_stuffed_fp16.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "..", "golden", "golden_render.npz"))
+    z = np.load(os.path.join(os.path.dirname(__file__), "..", "golden", "ckpt_lego_stuffed_fp16.npz"))
     cks = {"rand2": O.seeded_checkpoint(2), "semi30": O.seeded_checkpoint(2, 30.0), "trained11": O.trained_like_checkpoint(11),
            "lego": {"fine_model": {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files}}}
     poses = {"bench0": O.benchmark_pose(0, 3), "bench1": O.benchmark_pose(1, 3), "generic": O.generic_pose()}

@@ -350,3 +350,41 @@ def test_checkpoint_round_trip_reference_format(tmp_path, checkpoints, poses):
     num = sum(float((a - b).double().norm() ** 2) for a, b in zip(step.parameters(), step2.parameters()))
     den = sum(float(a.double().norm() ** 2) for a in step.parameters())
     assert (num / den) ** 0.5 <= 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_multi_chunk_batch_equals_its_chunks(mode):
+    """A batch larger than one workspace chunk (524,288 samples): 4600 rays x 128 samples = 588,800 samples run as a
+    full 4096-ray chunk plus a ragged 504-ray chunk inside ONE call (chunk-offset ray pointers, a smaller last chunk,
+    the pad-slab memsets, a fork/join of the auxiliary wgrad streams per chunk).  Gradients accumulate (+=) and are
+    scaled by the global ray count, so the call must equal the two chunks run as separate calls -- each of those fits
+    one chunk, the path every other test pins to the reference."""
+    from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host.synthetic import seeded_models
+    n, S = 4600, 128
+    g = torch.Generator().manual_seed(3)
+    ro = (torch.zeros(n, 3) + torch.tensor([0.0, 0.0, 4.0])).cuda()
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, -1.0]), dim=-1).cuda()
+    tgt, tr = torch.rand(n, 3, generator=g).cuda(), torch.rand(n, S, generator=g).cuda()
+
+    def run(parts):
+        _, fine = seeded_models(5, 30.0, "cuda")
+        total, first, rgbs = 0.0, 0, []
+        for count in parts:
+            sl = slice(first, first + count)
+            loss, rgb = ops.train_fwd_bwd(fine, ro[sl], rd[sl], tgt[sl], S, tr[sl].contiguous(), n_rays_global=n, mode=mode)
+            total += float(loss)
+            rgbs.append(rgb)
+            first += count
+        return total, [p.grad.double().clone() for p in fine.parameters()], torch.cat(rgbs), [k for k, _ in fine.named_parameters()]
+
+    with Watchdog() as wd:
+        l_one, g_one, rgb_one, names = run([n])
+        l_two, g_two, rgb_two, _ = run([4096, n - 4096])
+        torch.cuda.synchronize()
+        assert int(wd.word.item()) == 0, hex(int(wd.word.item()) & 0xffffffff)
+    assert abs(l_one - l_two) <= 1e-5 * abs(l_two)
+    assert torch.equal(rgb_one, rgb_two)
+    rel = sorted(((float((a - b).norm()) / max(float(b.norm()), 1e-30), k) for a, b, k in zip(g_one, g_two, names)), reverse=True)
+    print(f"mode {mode}: multi-chunk vs separate chunks, worst gradient tensors:", [(f"{e:.1e}", k) for e, k in rel[:3]])
+    assert rel[0][0] <= 1e-4, rel[0]              # summation order only (fp32 atomics / split reduction)

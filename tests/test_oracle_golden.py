@@ -76,6 +76,29 @@ def test_render_images_bit_exact(checkpoints, poses):
         assert np.array_equal(dep.numpy(), g[k + "|depth"]), k
 
 
+def test_config_size_goldens_bit_exact(checkpoints):
+    """BASELINE.json configs[1] / configs[2] sizes (tests/golden/make_golden_configs.py): the torch restatement, fed the
+    512-ray chunks render_image forms over a band, reproduces the reference's pixels bit for bit -- five rows of the
+    400x300x64 frame and rows 296-303 of the 800x600x128 frame."""
+    g = load_npz("golden_configs.npz")
+    for key, pose_key, w, h, s, row0, n, full in (("lego|view5of40|400x300x64", "pose_c2", 400, 300, 64, 148, 5, True),
+                                                  ("lego|view7of40|800x600x128|rows296+8", "pose_c3", 800, 600, 128, 296, 8, False)):
+        ro, rd = O.camera_rays(torch.from_numpy(g[pose_key]), w, h)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        first, last = row0 * w, (row0 + n) * w
+        c0, c1 = first // O.RENDER_CHUNK * O.RENDER_CHUNK, min(-(-last // O.RENDER_CHUNK) * O.RENDER_CHUNK, w * h)
+        with torch.no_grad():
+            parts = [O.render_rays(checkpoints["lego"]["fine_model"], ro[i:i + O.RENDER_CHUNK], rd[i:i + O.RENDER_CHUNK], s)[:2]
+                     for i in range(c0, c1, O.RENDER_CHUNK)]
+        out = [torch.cat([p[k] for p in parts]) for k in (0, 1)]
+        rgb, dep = out[0][first - c0:last - c0].reshape(n, w, 3).numpy(), out[1][first - c0:last - c0].reshape(n, w).numpy()
+        ref_rgb, ref_dep = g[key + "|rgb"], g[key + "|depth"]
+        if full:
+            ref_rgb, ref_dep = ref_rgb[row0:row0 + n], ref_dep[row0:row0 + n]
+        assert np.array_equal(rgb, ref_rgb) and np.array_equal(dep, ref_dep), key
+    assert g["lego|view5of40|400x300x64|rgb"].std() > 0.05 and g["semi30|view7of40|800x600x128|rows296+8|rgb"].max() > 0.1
+
+
 def test_fixtures_are_not_vacuous():
     """some seeds give sigma == 0 everywhere (black image, vacuous parity)."""
     g = load_npz("golden_render.npz")

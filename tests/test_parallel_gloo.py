@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nerf_dbr_b200.host.parallel import allreduce_sum_, gather_rows, ray_shard, row_band
+from nerf_dbr_b200.host.parallel import allreduce_sum_, broadcast_parameters_, gather_rows, ray_shard, row_band
 
 
 def test_row_bands_tile_the_image_exactly():
@@ -60,6 +60,25 @@ def _worker(rank, world, port, out):
             ok = ok and torch.equal(img, exp)
         else:
             ok = ok and img is None
+        # replica synchronisation (B200Trainer.__init__ / load_checkpoint): unseeded ranks construct different networks;
+        # after the broadcast they hold rank 0's, and one "step" (same all-reduced gradient, same update) keeps them equal
+        from nerf_dbr_b200.host.model import NeRFModel
+        torch.manual_seed(1000 + rank)
+        model = NeRFModel()
+        params = list(model.parameters())
+        broadcast_parameters_(params)
+        torch.manual_seed(1000)
+        ref_model = NeRFModel()
+        ok = ok and all(torch.equal(a, b) for a, b in zip(params, ref_model.parameters()))
+        grads = [torch.full_like(p, float(rank + 1)) for p in params]
+        allreduce_sum_(grads)
+        with torch.no_grad():
+            for p, gr in zip(params, grads):
+                p.add_(gr, alpha=-1e-3)
+        digest = torch.stack([p.detach().double().sum() for p in params]).sum().reshape(1)
+        both = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(both, digest)
+        ok = ok and all(torch.equal(b, both[0]) for b in both)
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
