@@ -2,7 +2,8 @@
 """bench.py -- BASELINE.json's headline metric: Mrays/s at 800x600, 128 samples/ray.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference (PyTorchCPURenderer) on the host cores
+    python bench.py --workload train|hierarchical ...        # configs[3] / configs[4] with their own metric names
 
 A step = one view of the 40-view synthetic orbit (reference benchmark_suite.py:132-149) rendered
 through the fused kernel: 480,000 rays x 128 samples = 61.44 M network queries = 64.865 TFLOP
@@ -89,68 +90,199 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline_sample(budget_s: float):
-    """The oracle port (torch CPU ops, the reference's algorithm and 512-ray chunks) on a bounded
-    band of view 0 of the same workload, all host threads."""
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core, so the
+    thread count is set explicitly (the round-1 scaling record's reference arm ran single-threaded at N > 1)."""
     import torch
-    from oracle import nerf_oracle as O
-    w = lego_weights()
-    pose = O.benchmark_pose(0, N_VIEWS)
-    ro, rd = O.camera_rays(pose, W, H)
-    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
-    with torch.no_grad():
-        O.render_rays(w, ro[:512], rd[:512], S)                      # warm the thread pool / allocator
+    n = host_cores()
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+class ReferenceCPU:
+    """The reference's own CPU implementation of the path, unmodified: ``PyTorchCPURenderer`` imported from the
+    vendored copy (oracle/_ref, tools/vendor_reference.sh) -- ``kind`` "reference".  When that copy is absent (a box
+    that never received it) the oracle port of the same algorithm stands in -- ``kind`` "port"."""
+
+    def __init__(self):
+        import torch
+        from oracle import refload
+        self.cores = use_all_host_threads()
+        self.weights = lego_weights()
+        self.kind, self.renderer = "port", None
+        if refload.reference_root() is not None:
+            try:
+                import tempfile
+                refload.import_reference()
+                from src.benchmark.pytorch_renderers import PyTorchCPURenderer
+                self._tmp = tempfile.TemporaryDirectory()
+                path = os.path.join(self._tmp.name, "lego_stuffed.pth")
+                torch.save({"coarse_model": self.weights, "fine_model": self.weights}, path)
+                r = PyTorchCPURenderer()
+                r.setup(path)
+                self.renderer, self.kind = r, "reference"
+            except Exception as e:  # noqa: BLE001 -- fall back to the port, say why
+                print(f"reference import failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+
+    def rays(self, pose, width=W, height=H):
+        import torch
+        with torch.no_grad():
+            if self.renderer is not None:
+                ro, rd = self.renderer.generate_rays(pose, width, height)
+            else:
+                from oracle import nerf_oracle as O
+                ro, rd = O.camera_rays(pose, width, height)
+        return ro.reshape(-1, 3), rd.reshape(-1, 3)
+
+    def render_first_rays(self, pose, n, samples=S):
+        """The first ``n`` rays of render_image(pose, (W, H), samples): the 512-ray chunks render_image itself forms
+        (pytorch_renderers.py:137-149), each through the reference's _render_ray_chunk."""
+        import torch
+        ro, rd = self.rays(pose)
+        with torch.no_grad():
+            for s0 in range(0, n, 512):
+                if self.renderer is not None:
+                    self.renderer._render_ray_chunk(ro[s0:min(s0 + 512, n)], rd[s0:min(s0 + 512, n)], samples)
+                else:
+                    from oracle import nerf_oracle as O
+                    O.render_rays(self.weights, ro[s0:min(s0 + 512, n)], rd[s0:min(s0 + 512, n)], samples)
+
+    def chunk_seconds(self, pose):
+        self.render_first_rays(pose, 512)                                 # warm the thread pool / allocator
         t0 = time.perf_counter()
-        O.render_rays(w, ro[:512], rd[:512], S)
-        probe = time.perf_counter() - t0
-        chunks = max(1, min(int(budget_s / max(probe, 1e-3)), W * H // 512))
-        n = chunks * 512
-        t0 = time.perf_counter()
-        for s in range(0, n, 512):
-            O.render_rays(w, ro[s:s + 512], rd[s:s + 512], S)
-        dt = time.perf_counter() - t0
-    return n, dt, torch.get_num_threads()
+        self.render_first_rays(pose, 512)
+        return max(time.perf_counter() - t0, 1e-3)
+
+
+def bench_pose(i):
+    """View i of the 40-view orbit as a fp32 4x4 (the product helper; equal to the reference's generate_test_poses,
+    tests/test_orbit_pose.py)."""
+    from nerf_dbr_b200.host.synthetic import orbit_pose
+    return orbit_pose(i % N_VIEWS, N_VIEWS)
+
+
+def cpu_baseline_sample(budget_s: float):
+    """cpu_baseline of the headline line: a bounded band of view 0 of the same workload, all host threads."""
+    ref = ReferenceCPU()
+    pose = bench_pose(0)
+    chunks = max(1, min(int(budget_s / ref.chunk_seconds(pose)), W * H // 512))
+    n = chunks * 512
+    t0 = time.perf_counter()
+    ref.render_first_rays(pose, n)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind,
+            "sample": f"first {n} rays of view 0 at 800x600x128 through PyTorchCPURenderer._render_ray_chunk, 512-ray chunks ({dt:.1f} s)"}
+
+
+def cpu_optimized_baseline():
+    """north_star: "the reference's PyTorch CPU and CPU_Optimized paths are timed on the same box's host cores".
+    CPUOptimizedRenderer.render_image has no chunking (cpu_optimized_renderer.py:187-223): every [R*S, 256] activation
+    of both networks is alive at once, ~9 GB at 200x150x32 and ~600 GB at 800x600x128 -- so it is timed at configs[0]
+    (200x150, 32 samples per ray) only, next to PyTorchCPURenderer at the same size for a like-for-like ratio."""
+    import tempfile
+    import torch
+    from oracle import refload
+    if refload.reference_root() is None:
+        return {"unavailable": "oracle/_ref not present on this box (tools/vendor_reference.sh)"}
+    cores = use_all_host_threads()
+    try:
+        refload.import_reference()
+        from src.benchmark.cpu_optimized_renderer import CPUOptimizedRenderer
+        from src.benchmark.pytorch_renderers import PyTorchCPURenderer
+        w = lego_weights()
+        out = {"unit": "Mrays/s", "cores": cores, "kind": "reference", "workload": "200x150, 32 samples/ray, view 0 (configs[0])"}
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "lego_stuffed.pth")
+            torch.save({"coarse_model": w, "fine_model": w}, path)
+            for key, cls in (("value", CPUOptimizedRenderer), ("pytorch_cpu_same_size", PyTorchCPURenderer)):
+                r = cls()
+                r.setup(path)
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    r.render_image(bench_pose(0), (200, 150), 32)
+                    out[key] = 200 * 150 / (time.perf_counter() - t0) / 1e6
+        out["sample"] = "one full 200x150x32 frame each (CPUOptimizedRenderer.render_image, PyTorchCPURenderer.render_image), no warm-up"
+        return out
+    except Exception as e:  # noqa: BLE001 -- a baseline must not take the headline down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def gpu_eager_baseline(dev):
+    """The reference's only GPU path on the same B200: PyTorchCUDARenderer (pytorch_renderers.py:173-246) -- eager torch
+    ops, cuBLAS SGEMM, 4096-ray chunks with a .cpu() per chunk -- at the headline size, TF32 off (torch's default, what
+    the reference runs) and on.  Library kernels: timed as a baseline only, never on this repo's path."""
+    import tempfile
+    import torch
+    from oracle import refload
+    if refload.reference_root() is None:
+        return {"unavailable": "oracle/_ref not present on this box (tools/vendor_reference.sh)"}
+    try:
+        refload.import_reference()
+        from src.benchmark.pytorch_renderers import PyTorchCUDARenderer
+        w = lego_weights()
+        out = {"unit": "Mrays/s", "kind": "reference", "renderer": "PyTorchCUDARenderer (eager torch, cuBLAS), chunk 4096",
+               "workload": "800x600x128, orbit views 0-2"}
+        keep = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        with tempfile.TemporaryDirectory() as tmp, torch.cuda.device(dev):
+            path = os.path.join(tmp, "lego_stuffed.pth")
+            torch.save({"coarse_model": w, "fine_model": w}, path)
+            r = PyTorchCUDARenderer()
+            r.setup(path)
+            for key, tf32 in (("value", False), ("value_tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                with torch.no_grad():
+                    r.render_image(bench_pose(0), (W, H), S)             # warm-up (cuBLAS handles, allocator)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for i in (1, 2):
+                        r.render_image(bench_pose(i), (W, H), S)
+                    torch.cuda.synchronize()
+                    out[key] = 2 * W * H / (time.perf_counter() - t0) / 1e6
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = keep
+        torch.cuda.empty_cache()
+        out["sample"] = "2 full frames after 1 warm-up per setting, wall clock around render_image (host image out, as the reference returns it)"
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for the path (oracle port; the reference is a
-    Python package that cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified PyTorchCPURenderer from the
+    vendored sources; the oracle port only if they are missing), all host threads whatever torchrun exported, a
+    bounded band of every view per step.  Rank 0 alone runs; other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle import nerf_oracle as O
-    w = lego_weights()
+    ref = ReferenceCPU()
     steps, warm = args.steps, args.warmup
     per_step_budget = min(3.0, 150.0 / max(1, steps + warm))
-    poses = [O.benchmark_pose(i % N_VIEWS, N_VIEWS) for i in range(steps + warm)]
-    with torch.no_grad():
-        ro, rd = O.camera_rays(poses[0], W, H)
-        O.render_rays(w, ro.reshape(-1, 3)[:512], rd.reshape(-1, 3)[:512], S)   # warm the thread pool
+    chunks = max(1, int(per_step_budget / ref.chunk_seconds(bench_pose(0))))
+    n = min(chunks * 512, W * H)
+    times = []
+    for i in range(steps + warm):
         t0 = time.perf_counter()
-        O.render_rays(w, ro.reshape(-1, 3)[:512], rd.reshape(-1, 3)[:512], S)
-        probe = time.perf_counter() - t0
-        chunks = max(1, int(per_step_budget / max(probe, 1e-3)))
-        n = min(chunks * 512, W * H)
-        times = []
-        for i, pose in enumerate(poses):
-            t0 = time.perf_counter()
-            ro, rd = O.camera_rays(pose, W, H)
-            ro, rd = ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]
-            for s in range(0, n, 512):
-                O.render_rays(w, ro[s:s + 512], rd[s:s + 512], S)
-            if i >= warm:
-                times.append(time.perf_counter() - t0)
+        ref.render_first_rays(bench_pose(i), n)                          # includes generate_rays of the whole view, as render_image does
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
     total = sum(times)
     value = n * steps / total / 1e6
-    sample = f"first {n} rays ({n // W} rows) of each 800x600x128 view, 512-ray chunks, fine network"
+    sample = (f"first {n} rays ({n / W:.1f} rows) of each 800x600x128 view: render_image's own 512-ray chunks through "
+              f"PyTorchCPURenderer._render_ray_chunk, fine network" if ref.kind == "reference" else
+              f"first {n} rays of each 800x600x128 view, oracle port of PyTorchCPURenderer (vendored reference sources absent)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "800x600x128 render, 40-view synthetic orbit (reference benchmark_suite.py:132-149)",
-                       "weights": "lego_stuffed_fp16 fixture", "sample_rays_per_step": n},
-            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+                       "weights": "lego_stuffed_fp16 fixture", "sample_rays_per_step": n,
+                       "host_threads": ref.cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
