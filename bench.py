@@ -312,74 +312,108 @@ def train_roofline(precision, n_samples, flop, ms):
                      "pre-activation gradients visit HBM once as bf16; write-only streams peak at 3.9 TB/s on this part")}
 
 
-def run_train(args):
-    """BASELINE.json configs[3]: 4096-ray batch, coarse 64 jittered + fine 128 uniform samples, forward + backward of
-    mse(coarse)+mse(fine), data-parallel (ray batch sharded, one NCCL gradient all-reduce) + Adam step.  Not the
-    headline metric -- printed with its own metric name."""
+def measure_train(dev, rank, world, weak, steps, warmup, precision, fused=True, transport="auto"):
+    """BASELINE.json configs[3]: 4096-ray batch (strong: in total; weak: per GPU), coarse 64 jittered + fine 128 uniform
+    samples, forward + backward of mse(coarse)+mse(fine), gradient exchange, clip, Adam, re-pack -- one iteration of
+    NeRFTrainer.train_step (trainer.py:83-138) per step.  ``fused``: TrainEngine (one CUDA graph of this library's
+    kernels, gradients summed over NVLink peer memory); else the unfused sequence (B200TrainStep + NCCL all-reduce +
+    torch's fused Adam).  A fresh batch is copied into the static input buffers inside the timed region every step.
+    Requires torch.distributed to be initialised when world > 1.  Returns the result dict (meaningful on rank 0)."""
     import torch
     import torch.distributed as dist
-    import nerf_dbr_b200 as nb
+    from nerf_dbr_b200.host import lib as L
     from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host.engine import TrainEngine
     from nerf_dbr_b200.host.parallel import ray_shard
+    from nerf_dbr_b200.host.synthetic import seeded_models
     from nerf_dbr_b200.host.trainer import B200TrainStep
 
-    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     n_c, n_f = 64, 128
-    n_rays = 4096 * (world if args.weak else 1)     # global batch: configs[3] (strong), or configs[3] per GPU (weak)
-    from nerf_dbr_b200.host.synthetic import seeded_models
-    coarse, fine = seeded_models(5, 30.0, dev)           # seeded default init, density heads x30 (semi-opaque volume)
-    from nerf_dbr_b200.host import lib as L
-    step = B200TrainStep(coarse, fine, n_c, n_f, mode=L.BF16 if args.precision == "bf16" else L.FP32)
-    opt = torch.optim.Adam(step.parameters(), lr=5e-4, fused=True)      # the reference's optimizer, PyTorch's fused kernel
+    n_rays = 4096 * (world if weak else 1)          # global batch: configs[3] (strong), or configs[3] per GPU (weak)
+    coarse, fine = seeded_models(5, 30.0, dev)      # seeded default init, density heads x30 (semi-opaque volume)
+    mode = L.BF16 if precision == "bf16" else L.FP32
     pose = torch.eye(4); pose[2, 3] = 4.0
     ro, rd = (t.cpu() for t in ops.generate_rays(pose, 200, 150, device=dev))
     g = torch.Generator().manual_seed(0)
     image = torch.rand(150, 200, 3, generator=g)
     first, count = ray_shard(rank, world, n_rays)
     batches = []
-    for i in range(args.steps + args.warmup):
+    for i in range(min(steps + warmup, 24)):        # a ring of distinct batches, resident in HBM
         sel = (torch.randperm(200 * 150, generator=g)[:n_rays] if n_rays <= 200 * 150 else
                torch.randint(0, 200 * 150, (n_rays,), generator=g))[first:first + count]
         batches.append((ro.reshape(-1, 3)[sel].to(dev), rd.reshape(-1, 3)[sel].to(dev), image.reshape(-1, 3)[sel].to(dev),
                         torch.rand(count, n_c, generator=g).to(dev)))
+    if fused:
+        eng = TrainEngine(coarse, fine, count, n_c, n_f, mode=mode, lr=5e-4, gamma=0.1 ** (1 / 250000), max_norm=1.0,
+                          n_rays_global=n_rays, transport=transport)
 
-    def one(i):
-        b = batches[i]
-        loss, _, _ = step(b[0], b[1], b[2], t_rand=b[3], n_rays_global=n_rays)
-        opt.step()
-        return loss
+        def one(i):
+            eng.step(*batches[i % len(batches)])
+        path = f"TrainEngine: CUDA graph, gradient exchange '{eng.transport}', fused clip+Adam+decay"
+    else:
+        step = B200TrainStep(coarse, fine, n_c, n_f, mode=mode)
+        opt = torch.optim.Adam(step.parameters(), lr=5e-4, fused=True)
 
-    for i in range(args.warmup):
+        def one(i):
+            b = batches[i % len(batches)]
+            step(b[0], b[1], b[2], t_rand=b[3], n_rays_global=n_rays)
+            torch.nn.utils.clip_grad_norm_(step.parameters(), 1.0)
+            opt.step()
+        path = "B200TrainStep + NCCL all-reduce + torch clip_grad_norm_ + torch fused Adam (eager launches)"
+
+    for i in range(warmup):
         one(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    torch.cuda.synchronize()
     n0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
-        loss = one(args.warmup + k)
+    for k in range(steps):
+        one(warmup + k)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
+        dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.steps
+    ms = float(t.item()) / steps
+    launches = int(ops.launch_count() - n0)
+    loss = eng.loss() if fused else None
+    graph = bool(eng.graph) if fused else False
+    if graph:                                           # replays do not pass through the library's host entry points:
+        launches = eng.launches_per_step * steps        # kernel nodes per replay (counted on the eager first step) x steps
+    flop = 3_095_808 * n_rays * (n_c + n_f)
+    out = {"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+exchange+clip+Adam",
+           "value": n_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+           "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fwd+bwd MSE, data-parallel gradient exchange, Adam",
+                      "global_rays": n_rays, "rays_per_gpu": count, "path": path, "cuda_graph": graph, "loss_last": loss,
+                      "inputs": "fresh batch copied device-to-device into the static buffers inside the timed region, every step"},
+           "gpu_launches": launches,
+           "kernels_per_step": (eng.launches_per_step if fused else launches // max(1, steps)),
+           "roofline": train_roofline(precision, n_rays * (n_c + n_f) // world, flop / world, ms)}      # per GPU
+    del batches
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args):
+    """--workload train: configs[3] with its own metric name (extra evidence; the default run carries the same numbers
+    under extras.train)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    out = measure_train(dev, rank, world, args.weak, args.steps, args.warmup, args.precision, fused=not args.unfused,
+                        transport=args.transport)
     if rank == 0:
-        flop = 3_095_808 * n_rays * (n_c + n_f)
-        emit({"metric": "training rays/s, 4096-ray batch, 64 coarse + 128 fine samples, fwd+bwd+Adam", "value": n_rays / (ms * 1e-3),
-              "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-              "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
-              "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-              "config": {"workload": "BASELINE.json configs[3]: 4096-ray batch fused fwd+bwd MSE, DP with NCCL grad allreduce",
-                         "global_rays": n_rays,
-                         "loss_last": float(loss)},
-              "gpu_launches": int(ops.launch_count() - n0),
-              "roofline": train_roofline(args.precision, n_rays * (n_c + n_f) // world, flop / world, ms)})      # per GPU
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -393,8 +427,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render = the headline metric (default); train = BASELINE.json configs[3], extra evidence")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "hierarchical"],
+                    help="render = the headline metric (default); train = BASELINE.json configs[3]; hierarchical = configs[4]")
+    ap.add_argument("--unfused", action="store_true", help="train workload: B200TrainStep + NCCL + torch Adam instead of TrainEngine")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "multimem", "nccl"],
+                    help="train workload: gradient exchange of TrainEngine")
+    ap.add_argument("--no-extras", action="store_true", help="render workload: skip extras.train and the extra baselines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -458,32 +496,60 @@ def main():
     total_ms = float(t.item())
     value = W * H * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- end to end through the public renderer API: host pose in, host image out --------------
+    # ---- end to end through the public renderer API: checkpoint file -> setup(); host poses in, host images out ----
+    import tempfile
     import nerf_dbr_b200 as nb
     r = nb.B200Renderer(args.precision, device_index=local)
-    r._packed = {"fine": net, "coarse": net}
-    host_rgb = torch.empty(n_rows, W, 3).pin_memory()
-    host_depth = torch.empty(n_rows, W).pin_memory()
+    with tempfile.TemporaryDirectory() as tmp:
+        ck = os.path.join(tmp, f"lego_stuffed_rank{rank}.pth")
+        torch.save({"coarse_model": weights, "fine_model": weights}, ck)
+        r.setup(ck)                                      # the reference's own entry: SharedNeRFModel + weight packing
     host_poses = [p.pin_memory() for p in poses]
-
-    def e2e_step(i):
-        g_rgb, g_depth = r.render_rows(host_poses[i], (W, H), S, row0, n_rows, out_rgb=rgb, out_depth=depth)
-        host_rgb.copy_(g_rgb, non_blocking=True)
-        host_depth.copy_(g_depth, non_blocking=True)
-        torch.cuda.synchronize()                         # the caller holds the image
-
-    for i in range(min(3, args.warmup)):
-        e2e_step(i)
+    checksum = 0.0
+    for rgb_h, _ in r.render_views(host_poses[:min(3, args.warmup)], (W, H), S, row0, n_rows):
+        checksum += float(rgb_h[0, 0, 0])
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(args.warmup + k)
+    for rgb_h, depth_h in r.render_views(host_poses[args.warmup:args.warmup + args.steps], (W, H), S, row0, n_rows):
+        checksum += float(rgb_h[0, 0, 0]) + float(depth_h[-1, -1])      # the caller touches every image it receives
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = W * H * args.steps / float(t.item()) / 1e6
+
+    # ---- thermally settled figure: 120 views back to back, no flush (1 s bursts flatter a power-capped part) ----
+    n_settle = 120
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(n_settle):
+        ops.render_image(net, poses[i % len(poses)], W, H, S, mode, row0=row0, n_rows=n_rows, out_rgb=rgb, out_depth=depth)
+    s1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    settled_value = W * H * n_settle / (float(t.item()) * 1e-3) / 1e6
+
+    # ---- configs[3] in the same record: training step, strong and weak data-parallel scaling (all ranks take part) ----
+    extras = {}
+    if not args.no_extras:
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            tr = {}
+            for tag, weak in (("strong", False), ("weak", True)):
+                if world == 1 and weak:
+                    continue                             # identical to strong at one GPU
+                m = measure_train(dev, rank, world, weak, 40, 8, "bf16")
+                tr[tag] = {k: m[k] for k in ("value", "unit", "ms_per_step", "gpu_launches", "kernels_per_step", "roofline", "config")}
+            extras["train"] = tr
+        except Exception as e:  # noqa: BLE001 -- extras must not take the headline down
+            extras["train"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -508,10 +574,13 @@ def main():
                                "fine network, uniform samples, image row bands sharded across GPUs",
                    "rays_per_step": W * H, "samples_per_ray": S, "msamples_per_s": value * S,
                    "weights": "lego_stuffed_fp16 fixture (tests/golden)", "l2": "flushed between timed steps (256 MiB memset)",
-                   "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+                   "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+                   "settled_mrays_per_s_120_views": settled_value,
+                   "settled_note": "120 views back to back, one pair of CUDA events, no L2 flush: the power-capped steady state"},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 64,
                 "d2h_bytes_per_step": n_rows * W * 16,
-                "path": "B200Renderer.render_rows(host pose) -> pinned host rgb+depth, wall clock incl. sync"},
+                "path": "B200Renderer.setup(checkpoint.pth); B200Renderer.render_views(host poses) -> pinned host rgb+depth per "
+                        "view (copy of view k overlaps the render of view k+1), wall clock over all views incl. the last copy"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -520,10 +589,13 @@ def main():
                      "peak_source": pk["source"] + ", burst cuBLAS bf16",
                      "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None},
     }
+    if extras:
+        line["extras"] = extras
     if world == 1 and not args.no_cpu_baseline:
-        n, dt, cores = cpu_baseline_sample(12.0)
-        line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                "sample": f"first {n} rays of view 0 at 800x600x128, 512-ray chunks ({dt:.1f} s)"}
+        line["cpu_baseline"] = cpu_baseline_sample(12.0)
+        if not args.no_extras:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
+            line["cpu_baseline_optimized"] = cpu_optimized_baseline()
     emit(line)
     if world > 1:
         dist.destroy_process_group()

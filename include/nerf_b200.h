@@ -165,6 +165,32 @@ NERF_B200_API int nerf_b200_render_rays_ex(const void *packed, const float *rays
 NERF_B200_API int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_rays, int n_sorted, int n_new,
                             float *z_out, void *stream);
 
+/* hierarchical_samples: the sampling side of a coarse -> importance -> fine render (BASELINE.json configs[4]) as ONE
+ * kernel: VolumeRenderer.sample_points_on_rays (the coarse depths: uniform, or stratified with t_rand [n_rays,n_samples])
+ * + VolumeRenderer.importance_sample (src/utils/rendering.py:54-100, with the shape fix; `weights` [n_rays,n_samples]
+ * = the coarse pass's compositing weights, e.g. weights_out of render_rays_ex) + the sorted union.  Only
+ * z_out [n_rays, n_samples + n_new] is written: bit for bit merge_samples(z, importance_sample(z, weights, u).z_new)
+ * with z = sample_points(..).z_vals.  u [n_rays,n_new] = the uniforms of rendering.py:79; u == NULL draws them in the
+ * kernel (Philox4x32-10, key `seed`, 24-bit mantissas like torch.rand).  n_samples % 32 == 0, both counts <= 1024. */
+NERF_B200_API int nerf_b200_hierarchical_samples(const float *weights, int n_rays, int n_samples, int n_new, float near,
+                                   float far, const float *t_rand, const float *u, uint64_t seed, float *z_out,
+                                   void *stream);
+
+/* ---- data path ---------------------------------------------------------------------------
+ * composite_white: the per-image conversion of SyntheticDataset.__init__ (src/data/loader.py:46-54) for RGBA8 pixels
+ * already resized on the host: img/255 in float64, rgb*alpha + (1-alpha), stored as fp32 -- bit-exact with the
+ * reference's numpy float64 arithmetic followed by torch.FloatTensor.  rgba [n_pixels,4] uint8 (device) ->
+ * rgb_out [n_pixels,3] fp32. */
+NERF_B200_API int nerf_b200_composite_white(const unsigned char *rgba, int64_t n_pixels, float *rgb_out, void *stream);
+
+/* ray_batch: the ray selection of NeRFTrainer.train_step (src/training/trainer.py:100-118): for pixel_index [n]
+ * (int64, row-major pixel = row * width + col, device) -> rays_o, rays_d [n,3] with the bits of
+ * _get_rays(pose, (H, W), focal)[index] (trainer.py:271-292; SyntheticDataset.get_rays, loader.py:78-108) and, when
+ * `target` != NULL, target [n,3] = image[index] gathered from image [H*W,3] (device).  The full-image ray tensors the
+ * reference builds every step never exist. */
+NERF_B200_API int nerf_b200_ray_batch(const float *c2w_host, int width, int height, float focal, const int64_t *pixel_index,
+                        int n, const float *image, float *rays_o, float *rays_d, float *target, void *stream);
+
 /* ---- training ----------------------------------------------------------------------------
  * train_fwd_bwd: forward + backward of ONE network's term of the photometric loss in
  * NeRFTrainer.train_step (src/training/trainer.py:117-126):
@@ -196,6 +222,55 @@ NERF_B200_API int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200
                                float near, float far, const float *t_rand, int n_rays_global,
                                int mode, void *workspace, float *loss_sum, float *rgb_out,
                                int phases, int sm_limit, void *stream);
+
+/* ---- optimizer step + data-parallel gradient exchange -------------------------------------------
+ * Replaces the tail of NeRFTrainer.train_step (src/training/trainer.py:125-136): clip_grad_norm_ over both networks,
+ * Adam.step() (weight_decay = L2 in the gradient), and -- new, the reference is single-device -- the sum of the
+ * gradients over data-parallel ranks, done by this library's own kernels over NVLink peer memory instead of a
+ * collective library call.
+ *
+ * All parameters of a step live in ONE flat fp32 bucket; gradients, exp_avg and exp_avg_sq likewise (same offsets).
+ * The gradient bucket G and the reduced bucket Gsum sit in a SYMMETRIC allocation of nerf_b200_dp_bytes(n) bytes per
+ * rank, laid out [ctl: NERF_B200_DP_CTL_BYTES | G: n floats | Gsum: n floats], zero-initialised, which every rank maps
+ * from every other rank (the caller obtains the mappings, e.g. torch symmetric memory; `peer[q]` is rank q's
+ * allocation as mapped in THIS process, `multicast` optionally the NVSwitch multicast mapping of the same
+ * allocation).  n must be a multiple of 4 * world; floats [0, n_opt) are parameters' gradients (zero in the pads),
+ * floats [n_opt, n) ride along un-optimised (slot n_opt carries the loss).  `state`: NERF_B200_DP_STATE_BYTES of
+ * zeroed private device memory per rank.
+ *
+ *   nerf_b200_dp_reduce     after the backward kernels on the same stream: waits until every rank's G is final, sums
+ *                           this rank's 1/world shard over the ranks in rank order (or with one in-switch
+ *                           multimem.ld_reduce when `multicast` is set) and stores the sums into every rank's Gsum.
+ *   nerf_b200_dp_adam_step  waits until every shard arrived; gradient norm, clip (max_norm <= 0: off), Adam on the
+ *                           whole bucket, G zeroed for the next step.  hyper (device, 8 DOUBLES, static): lr0, gamma,
+ *                           beta1, beta2, eps, weight_decay, max_norm, loss_scale.  The step count t lives on the
+ *                           device (`state`, uint32 at byte offset NERF_B200_DP_STATE_OPT_STEP; the kernel increments
+ *                           it; the host sets it on resume): lr_t = lr0 gamma^t (ExponentialLR stepped once per
+ *                           iteration, trainer.py:62-64,136) and Adam's 1 - beta^(t+1) are formed in the kernel, so a
+ *                           step costs no host-to-device traffic and the launch pair can sit in a CUDA graph.
+ *                           loss_out (device, 3 floats, optional): [0] = summed slot n_opt * loss_scale, [1] = gradient
+ *                           norm before clipping, [2] = the learning rate used.
+ *
+ * Every rank computes the same bits (fixed summation order, replicated update).  world == 1 needs no peer: pass
+ * peer[0] = the local allocation.  Every rank must call both functions once per step, in this order; a rank that
+ * never arrives makes the others trap after ~20 s instead of hanging.  `emulate_sequential` (tests): no flag waits --
+ * several "ranks" whose allocations live on one GPU are run as reduce(0..W-1) then adam_step(0..W-1) on one stream. */
+#define NERF_B200_DP_MAX_WORLD 16
+#define NERF_B200_DP_CTL_BYTES 1024
+#define NERF_B200_DP_STATE_BYTES 1024
+#define NERF_B200_DP_STATE_OPT_STEP 12
+typedef struct nerf_b200_dp {
+    int rank, world;
+    int64_t n, n_opt;
+    void *peer[NERF_B200_DP_MAX_WORLD];
+    void *multicast;
+    void *state;
+    int emulate_sequential;
+} nerf_b200_dp;
+NERF_B200_API size_t nerf_b200_dp_bytes(int64_t n);
+NERF_B200_API int nerf_b200_dp_reduce(const nerf_b200_dp *dp_host, void *stream);
+NERF_B200_API int nerf_b200_dp_adam_step(const nerf_b200_dp *dp_host, float *params, float *exp_avg, float *exp_avg_sq,
+                           const double *hyper, float *loss_out, void *stream);
 
 /* Environment (read ONCE per process, at the first tensor-core render launch; for A/B measurements only):
  * NERF_B200_CLUSTER=1 makes every CTA stream the whole weight set itself instead of sharing the stream inside 2-CTA

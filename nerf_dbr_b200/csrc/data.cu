@@ -1,0 +1,81 @@
+// Data path on the device: what SyntheticDataset does per image on the host in float64
+// (src/data/loader.py:42-64) and what NeRFTrainer.train_step does per iteration with full-image tensors
+// (src/training/trainer.py:100-118, 271-292).
+//
+//   composite_white_kernel   RGBA8 pixels -> fp32 RGB on a white background, bit for bit the reference's
+//                            float64 arithmetic rounded once to fp32: c = r/255, a = A/255, fl32(c*a + (1 - a)).
+//                            4 bytes in, 12 bytes out per pixel: the images cross PCIe as uint8, a sixth of the float64
+//                            arrays the reference builds.
+//   ray_batch_kernel         the ray batch of a training step straight from the pixel indices: origins, directions
+//                            (the same bits as _get_rays(pose)[index]) and target colours gathered from the
+//                            device-resident image -- the full-image ray tensors (24 B per pixel per step) never exist.
+#include "common.cuh"
+#include <algorithm>
+
+namespace nerfb200 {
+
+__global__ void __launch_bounds__(256) composite_white_kernel(const uchar4 *__restrict__ rgba, size_t n, float *__restrict__ rgb)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uchar4 p = __ldg(rgba + i);
+        // numpy: img / 255.0 (float64), rgb * alpha + (1 - alpha): three roundings, no contraction
+        const double a = __ddiv_rn((double)p.w, 255.0), ia = __dsub_rn(1.0, a);
+        rgb[3 * i + 0] = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)p.x, 255.0), a), ia));
+        rgb[3 * i + 1] = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)p.y, 255.0), a), ia));
+        rgb[3 * i + 2] = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)p.z, 255.0), a), ia));
+    }
+}
+
+__global__ void __launch_bounds__(256) ray_batch_kernel(Pose pose, int width, float half_w, float half_h, float focal,
+                                                        const long long *__restrict__ index, int n, const float *__restrict__ image,
+                                                        float *__restrict__ rays_o, float *__restrict__ rays_d, float *__restrict__ target)
+{
+    const int total = 3 * n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int r = e / 3, c = e - 3 * r;
+        const long long pix = __ldg(index + r);
+        const int j = (int)(pix / width), i = (int)(pix - (long long)j * width);
+        float dx, dy;
+        pixel_dir(i, j, half_w, half_h, focal, dx, dy);
+        rays_d[e] = rotate_dir(pose, c, dx, dy);
+        rays_o[e] = pose.t[c];
+        if (target) target[e] = __ldg(image + 3 * pix + c);
+    }
+}
+
+}  // namespace nerfb200
+
+using namespace nerfb200;
+
+static int blocks_for(size_t items)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)sms * 8));
+}
+
+extern "C" {
+
+int nerf_b200_composite_white(const unsigned char *rgba, int64_t n_pixels, float *rgb_out, void *stream)
+{
+    if (!rgba || !rgb_out || n_pixels <= 0) return NERF_B200_EINVAL;
+    if ((uintptr_t)rgba & 3) return NERF_B200_EALIGN;
+    composite_white_kernel<<<blocks_for((size_t)n_pixels), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uchar4 *>(rgba), (size_t)n_pixels, rgb_out);
+    return launch_status();
+}
+
+int nerf_b200_ray_batch(const float *c2w_host, int width, int height, float focal, const int64_t *pixel_index, int n,
+                        const float *image, float *rays_o, float *rays_d, float *target, void *stream)
+{
+    if (!c2w_host || !pixel_index || !rays_o || !rays_d || width <= 0 || height <= 0 || n <= 0 || !(focal > 0.f) ||
+        (target && !image))
+        return NERF_B200_EINVAL;
+    ray_batch_kernel<<<blocks_for((size_t)n * 3), 256, 0, (cudaStream_t)stream>>>(
+        pose_from_c2w(c2w_host), width, (float)((double)width * 0.5), (float)((double)height * 0.5), focal,
+        reinterpret_cast<const long long *>(pixel_index), n, image, rays_o, rays_d, target);
+    return launch_status();
+}
+
+}  // extern "C"

@@ -322,6 +322,131 @@ __global__ void merge_samples_kernel(const float *__restrict__ z_a, const float 
     }
 }
 
+// ------------------------------------------------------------------------------ hierarchical sampling, fused
+// coarse depths (uniform / stratified, computed -- never read) + inverse-CDF importance samples + sorted union in ONE
+// kernel: the only per-sample stream that leaves the SM is the union z_all [R, S + n_new] the fine pass renders.
+// Replaces the launch sequence sample_points -> importance_sample -> merge_samples (whose intermediate z_vals, z_new,
+// indices and points crossed HBM between launches); the arithmetic of each stage is the same bit for bit:
+// sample_points_kernel's depths, importance_kernel's exact-order cdf and lerp, merge_samples_kernel's bitonic sort and
+// rank merge.  reference: VolumeRenderer.sample_points_on_rays + importance_sample, src/utils/rendering.py:17-100.
+// `u` == nullptr draws the uniforms in the kernel (Philox4x32-10 keyed by `seed`, counter = ray, sample / 4):
+// throughput runs; parity runs pass the captured tensor (torch.rand cannot be reproduced on the device).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__global__ void __launch_bounds__(256) hierarchical_samples_kernel(const float *__restrict__ weights, const float *__restrict__ t_rand,
+                                                                   const float *__restrict__ u, unsigned long long seed, int n_rays,
+                                                                   int n_samples, int n_new, int nb_pow2, int group, float near,
+                                                                   float far, float *__restrict__ z_out)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = (2 * n_samples + 1 + nb_pow2) | 1;       // odd: [S+1] cdf, [S] z, [nb_pow2] new samples
+    const float step = linspace_step(n_samples);
+    for (int base = blockIdx.x * group; base < n_rays; base += gridDim.x * group) {
+        // ---- phase 1 (warp per ray): w + 1e-5, its exact-order total, the quotients; the coarse depths
+        for (int q = warp; q < group; q += 8) {
+            const int ray = base + q;
+            if (ray >= n_rays) continue;
+            float *cdf = smem + (size_t)q * pitch, *zs = cdf + n_samples + 1;
+            const float *w = weights + (size_t)ray * n_samples;
+            float part = 0.0f;
+            for (int s = lane; s < n_samples; s += 32) {
+                const float v = __fadd_rn(__ldg(w + s), 1e-5f);
+                cdf[s + 1] = v;
+                zs[s] = t_rand ? depth_jittered(s, n_samples, step, near, far, __ldg(t_rand + (size_t)ray * n_samples + s))
+                               : depth_uniform(s, n_samples, step, near, far);
+                part = __fadd_rn(part, v);
+            }
+            const float a1 = __shfl_sync(0xffffffffu, part, (lane & 7) + 8);
+            const float a2 = __shfl_sync(0xffffffffu, part, (lane & 7) + 16);
+            const float a3 = __shfl_sync(0xffffffffu, part, (lane & 7) + 24);
+            const float a0 = __shfl_sync(0xffffffffu, part, (lane & 7));
+            const float l8 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+            float total = __shfl_sync(0xffffffffu, l8, 0);
+#pragma unroll
+            for (int l = 1; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, l8, l));
+            for (int s = lane; s < n_samples; s += 32) cdf[s + 1] = __fdiv_rn(cdf[s + 1], total);
+        }
+        __syncthreads();
+        // ---- phase 2 (thread per ray): the serial double-precision running sum, 32 rays at once
+        if (warp == 0 && lane < group && base + lane < n_rays) {
+            float *cdf = smem + (size_t)lane * pitch;
+            double run = 0.0;
+            cdf[0] = 0.0f;
+            for (int s = 1; s <= n_samples; ++s) {
+                run += (double)cdf[s];
+                cdf[s] = (float)run;
+            }
+        }
+        __syncthreads();
+        // ---- phases 3 + 4 (warp per ray): inverse-CDF samples into shared memory, bitonic sort, rank merge -> z_out
+        for (int q = warp; q < group; q += 8) {
+            const int ray = base + q;
+            if (ray >= n_rays) continue;
+            const float *cdf = smem + (size_t)q * pitch, *a = cdf + n_samples + 1;
+            float *b = smem + (size_t)q * pitch + 2 * n_samples + 1;
+            for (int k0 = 0; k0 < nb_pow2; k0 += 32) {
+                const int k = k0 + lane;
+                float z = __int_as_float(0x7f800000);              // +inf pads the sort to a power of two
+                if (k < n_new) {
+                    float uk;
+                    if (u) {
+                        uk = __ldg(u + (size_t)ray * n_new + k);
+                    } else {
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)ray, (uint32_t)(k >> 2), 0u, 0u),
+                                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                        const uint32_t bits = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
+                        uk = (float)(bits >> 8) * 5.9604644775390625e-08f;      // [0, 1): 24 random bits, as torch.rand
+                    }
+                    int lo = 0, hi = n_samples + 1;                // first index with cdf > u (right=True)
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= uk) lo = mid + 1; else hi = mid; }
+                    const int below = min(max(lo - 1, 0), n_samples - 1), above = min(lo, n_samples - 1);
+                    float den = __fsub_rn(cdf[above], cdf[below]);
+                    if (den < 1e-5f) den = 1.0f;
+                    const float t = __fdiv_rn(__fsub_rn(uk, cdf[below]), den);
+                    z = __fadd_rn(a[below], __fmul_rn(t, __fsub_rn(a[above], a[below])));
+                }
+                if (k < nb_pow2) b[k] = z;
+            }
+            __syncwarp();
+            for (int k = 2; k <= nb_pow2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (nb_pow2 >> 1); t += 32) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                        const float x = b[lo], y = b[hi];
+                        const bool up = (lo & k) == 0;
+                        if ((x > y) == up) { b[lo] = y; b[hi] = x; }
+                    }
+                    __syncwarp();
+                }
+            float *out = z_out + (size_t)ray * (n_samples + n_new);
+            for (int i = lane; i < n_samples; i += 32) {       // rank = i + #{b < a_i}
+                const float v = a[i];
+                int lo = 0, hi = n_new;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if (b[m] < v) lo = m + 1; else hi = m; }
+                out[i + lo] = v;
+            }
+            for (int i = lane; i < n_new; i += 32) {           // rank = i + #{a <= b_i}
+                const float v = b[i];
+                int lo = 0, hi = n_samples;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
+                out[i + lo] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 static inline int grid_for(size_t work_items, int block, int per_sm = 8)
 {
     int dev = 0, sms = 148;
@@ -418,6 +543,29 @@ int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_ray
     }
     merge_samples_kernel<<<grid_for((size_t)n_rays * 32, block, 12), block, smem, (cudaStream_t)stream>>>(
         z_sorted, z_new, n_rays, n_sorted, n_new, pow2, z_out);
+    return launch_status();
+}
+
+int nerf_b200_hierarchical_samples(const float *weights, int n_rays, int n_samples, int n_new, float near, float far,
+                                   const float *t_rand, const float *u, uint64_t seed, float *z_out, void *stream)
+{
+    if (!weights || !z_out || n_rays <= 0 || n_samples <= 0 || n_new <= 0) return NERF_B200_EINVAL;
+    if (n_samples % 32 != 0 || n_samples > 1024 || n_new > 1024) return NERF_B200_EUNSUPPORTED;
+    int pow2 = 1;
+    while (pow2 < n_new) pow2 <<= 1;
+    const int block = 256;
+    const int pitch = (2 * n_samples + 1 + pow2) | 1;
+    int group = 32;
+    while (group > 8 && (size_t)group * pitch * sizeof(float) > 96 * 1024) group >>= 1;
+    const size_t smem = (size_t)group * pitch * sizeof(float);
+    if (smem > 200 * 1024) return NERF_B200_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hierarchical_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+    hierarchical_samples_kernel<<<grid_for(((size_t)n_rays + group - 1) / group * block, block, per_sm), block, smem, (cudaStream_t)stream>>>(
+        weights, t_rand, u, (unsigned long long)seed, n_rays, n_samples, n_new, pow2, group, near, far, z_out);
     return launch_status();
 }
 

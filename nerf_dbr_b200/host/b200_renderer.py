@@ -93,6 +93,43 @@ class B200Renderer(_Base):
                                                    n_coarse, n_importance, self.mode, self.near, self.far, u)
         return rgb.reshape(height, width, 3), depth.reshape(height, width)
 
+    def render_views(self, camera_poses, resolution: Tuple[int, int], samples_per_ray: int = 64, row0: int = 0,
+                     n_rows=None):
+        """Generator over a sequence of views (the suite's orbit, benchmark_suite.py:180-192): yields
+        ``(rgb [n_rows,W,3], depth [n_rows,W])`` as PINNED HOST tensors, one view behind the GPU -- while view k is copied
+        to the host on a second stream, view k+1 is already rendering, and the host only ever waits for a finished copy.
+        Two buffer sets alternate: a yielded pair stays valid until the next-but-one ``next()``."""
+        width, height = resolution
+        n_rows = height - row0 if n_rows is None else n_rows
+        dev = self._torch_device
+        with torch.cuda.device(dev):
+            main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
+            sets = []
+            for _ in range(2):
+                sets.append({"rgb": torch.empty(n_rows, width, 3, device=dev), "depth": torch.empty(n_rows, width, device=dev),
+                             "h_rgb": torch.empty(n_rows, width, 3).pin_memory(), "h_depth": torch.empty(n_rows, width).pin_memory(),
+                             "rendered": torch.cuda.Event(), "copied": torch.cuda.Event()})
+            pending = None
+            for i, pose in enumerate(camera_poses):
+                b = sets[i & 1]
+                if i >= 2:
+                    main.wait_event(b["copied"])                         # the device buffers of this set are free again
+                ops.render_image(self._net(True), pose, width, height, samples_per_ray, self.mode, 800.0, self.near, self.far,
+                                 row0, n_rows, b["rgb"], b["depth"])
+                b["rendered"].record(main)
+                side.wait_event(b["rendered"])
+                with torch.cuda.stream(side):
+                    b["h_rgb"].copy_(b["rgb"], non_blocking=True)
+                    b["h_depth"].copy_(b["depth"], non_blocking=True)
+                    b["copied"].record(side)
+                if pending is not None:
+                    pending["copied"].synchronize()
+                    yield pending["h_rgb"], pending["h_depth"]
+                pending = b
+            if pending is not None:
+                pending["copied"].synchronize()
+                yield pending["h_rgb"], pending["h_depth"]
+
     def render_rows(self, camera_pose, resolution: Tuple[int, int], samples_per_ray: int, row0: int, n_rows: int,
                     out_rgb=None, out_depth=None):
         """The multi-GPU shard: rows [row0, row0+n_rows) of the image."""

@@ -3,9 +3,11 @@
 (``{'image': [H,W,3], 'pose': [4,4], 'focal': float}``), same per-step order -- random ray selection, coarse
 (stratified) + fine (uniform) render, ``mse + mse``, optional ``clip_grad_norm_``, Adam, exponential LR decay --
 same checkpoint format and resume rule.  What differs is where the work runs: rays, both networks' forward and
-backward and the full-image validation render are ``nerf_b200_*`` calls; optimizer, clipping and scheduler stay
-PyTorch on the same ``nn.Parameter``s (trainer.py:125-136).  Data parallel when ``torch.distributed`` is
-initialised: every rank draws the same ray selection, trains on its shard, gradients are all-reduced."""
+backward and the full-image validation render are ``nerf_b200_*`` calls.  By default (``fused_step``) the gradient
+exchange, clipping, Adam and the learning-rate decay are this library's kernels too and the whole iteration is one CUDA
+graph (``TrainEngine``); with ``fused_step: False`` optimizer, clipping and scheduler are plain PyTorch on the same
+``nn.Parameter``s (trainer.py:125-136) and the gradients are all-reduced with NCCL.  Data parallel when
+``torch.distributed`` is initialised: every rank draws the same ray selection and trains on its shard."""
 from __future__ import annotations
 
 import math
@@ -19,6 +21,7 @@ from . import lib as L
 from . import ops
 from .model import NeRFModel
 from .parallel import broadcast_parameters_, ray_shard
+from .engine import TrainEngine
 from .trainer import B200TrainStep, load_checkpoint, save_checkpoint
 
 
@@ -33,7 +36,8 @@ class B200Trainer:
     """Mirror of ``NeRFTrainer`` (trainer.py:18-81).  ``config`` keys read: hidden_dim / position_encoding_levels /
     direction_encoding_levels (must be the reference's 256 / 10 / 4: the kernels are specialised for that network),
     lr, weight_decay, lr_decay, decay_steps, n_coarse, n_fine, n_rays, near, far, gradient_clipping,
-    checkpoint_frequency, plus ``precision`` ('bf16' | 'fp32'), ``device_index`` (default: ``$LOCAL_RANK``, else the current device), ``seed``,
+    checkpoint_frequency, plus ``fused_step`` (default True), ``dp_transport`` ('auto' | 'p2p' | 'multimem' | 'nccl'),
+    ``precision`` ('bf16' | 'fp32'), ``device_index`` (default: ``$LOCAL_RANK``, else the current device), ``seed``,
     ``checkpoint_dir`` (default 'checkpoints', as the reference)."""
 
     def __init__(self, config: Dict):
@@ -68,12 +72,42 @@ class B200Trainer:
         self.step_fn = B200TrainStep(self.coarse_model, self.fine_model, self.n_coarse, self.n_fine, self.near, self.far,
                                      mode=self.mode)
         self.train_losses, self.val_losses = [], []
+        self.fused_step = bool(config.get("fused_step", True))
+        self._loaded_state = False
+        self.engine: Optional[TrainEngine] = None          # built at the first step, when the batch size is known
         # ray selection and jitter: one generator, identical on every rank (each rank then takes its shard)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(seed) if seed is not None else 0)
 
     # ------------------------------------------------------------------ one step (trainer.py:83-138)
-    def train_step(self, batch: Dict) -> float:
+    def _engine_for(self, n_rays: int) -> TrainEngine:
+        rank, world = _dist()
+        count = ray_shard(rank, world, n_rays)[1]
+        if self.engine is None or self.engine.n_rays != count or self.engine.n_rays_global != n_rays:
+            if world > 1 and any(ray_shard(r, world, n_rays)[1] != count for r in range(world)):
+                raise ValueError(f"fused_step needs n_rays ({n_rays}) divisible by the world size ({world})")
+            cfg, t = self.config, (self.engine.opt_step if self.engine is not None else None)
+            if self.engine is not None:
+                self.engine.sync_holders()
+            previous = (self.optimizer, self.scheduler) if self.engine is not None or self._loaded_state else None
+            self.engine = TrainEngine(self.coarse_model, self.fine_model, count, self.n_coarse, self.n_fine, self.near, self.far,
+                                      mode=self.mode, lr=cfg.get("lr", 5e-4),
+                                      gamma=cfg.get("lr_decay", 0.1) ** (1 / cfg.get("decay_steps", 250000)),
+                                      weight_decay=cfg.get("weight_decay", 0.0), max_norm=self.gradient_clipping,
+                                      n_rays_global=n_rays, transport=cfg.get("dp_transport", "auto"))
+            if previous is not None:                         # carry Adam moments / step count over (resume, or a new batch size)
+                self.engine.optimizer.load_state_dict(previous[0].state_dict())
+                self.engine.scheduler.load_state_dict(previous[1].state_dict())
+                self.engine.adopt_holders()
+                if t is not None:
+                    self.engine.opt_step = t
+            self.optimizer, self.scheduler = self.engine.optimizer, self.engine.scheduler
+            self.step_fn.coarse, self.step_fn.fine = self.coarse_model, self.fine_model
+        return self.engine
+
+    def train_step(self, batch: Dict, sync: bool = True):
+        """One iteration (trainer.py:83-138).  Returns the loss as a float like the reference; ``sync=False`` returns a
+        0-dim device tensor instead and does not wait for the GPU."""
         self.coarse_model.train()
         self.fine_model.train()
         image = batch["image"].to(self.device, torch.float32)
@@ -86,13 +120,18 @@ class B200Trainer:
         rank, world = _dist()
         first, count = ray_shard(rank, world, n_rays)
         sel = select[first:first + count]
+        if self.fused_step:
+            eng = self._engine_for(n_rays)
+            eng.step(rays_o[sel], rays_d[sel], target[sel], t_rand[first:first + count])
+            loss = eng.out[0].clone()
+            return float(loss) if sync else loss
         loss, _, _ = self.step_fn(rays_o[sel], rays_d[sel], target[sel], t_rand=t_rand[first:first + count].contiguous(),
                                   n_rays_global=n_rays)
         if self.gradient_clipping is not None:
             torch.nn.utils.clip_grad_norm_(self.step_fn.parameters(), self.gradient_clipping)
         self.optimizer.step()
         self.scheduler.step()
-        return float(loss)
+        return float(loss) if sync else loss.detach()
 
     # ------------------------------------------------------------------ validation (trainer.py:140-170, 355-372)
     def render_image(self, pose: torch.Tensor, img_shape, focal: float) -> torch.Tensor:
@@ -121,8 +160,8 @@ class B200Trainer:
             say(f"Resuming from {latest}: {len(self.train_losses)}/{n_epochs} epochs done")
         start = len(self.train_losses)
         for epoch in range(start, n_epochs):
-            losses = [self.train_step(train_dataset[i]) for i in range(len(train_dataset))]
-            self.train_losses.append(float(sum(losses) / max(len(losses), 1)))
+            losses = [self.train_step(train_dataset[i], sync=False) for i in range(len(train_dataset))]      # no read-back per step
+            self.train_losses.append(float(torch.stack(losses).mean()) if losses else 0.0)                  # one per epoch
             if val_dataset is not None and (epoch + 1) % 10 == 0:
                 self.val_losses.append(self.validate(val_dataset))
                 say(f"Epoch {epoch + 1}: train {self.train_losses[-1]:.4f}, val {self.val_losses[-1]:.4f}")
@@ -142,6 +181,8 @@ class B200Trainer:
         return best[1] if best else None
 
     def save_checkpoint(self, filename: str) -> str:
+        if self.engine is not None:
+            self.engine.sync_holders()                      # step count / lr of the device-resident schedule into the torch objects
         os.makedirs(self.checkpoint_dir, exist_ok=True)
         path = os.path.join(self.checkpoint_dir, filename)
         save_checkpoint(path, self.step_fn, self.optimizer, self.scheduler, self.config, self.train_losses, self.val_losses)
@@ -150,6 +191,9 @@ class B200Trainer:
     def load_checkpoint(self, path: str) -> None:
         self.train_losses, self.val_losses = (list(x) for x in load_checkpoint(path, self.step_fn, self.optimizer, self.scheduler))
         broadcast_parameters_(self.step_fn.parameters())       # replicas restart identical even if only rank 0's file is current
+        self._loaded_state = True
+        if self.engine is not None:
+            self.engine.adopt_holders()
 
     @staticmethod
     def psnr(mse: float) -> float:

@@ -34,6 +34,16 @@ class Params(ctypes.Structure):
                 ("color1_w", c_void_p), ("color1_b", c_void_p)]
 
 
+DP_MAX_WORLD, DP_CTL_BYTES, DP_STATE_BYTES, DP_STATE_OPT_STEP = 16, 1024, 1024, 12
+
+
+class DP(ctypes.Structure):
+    """nerf_b200_dp: the data-parallel exchange's addresses (include/nerf_b200.h)."""
+    _fields_ = [("rank", c_int), ("world", c_int), ("n", c_int64), ("n_opt", c_int64),
+                ("peer", c_void_p * DP_MAX_WORLD), ("multicast", c_void_p), ("state", c_void_p),
+                ("emulate_sequential", c_int)]
+
+
 # every symbol include/nerf_b200.h declares: name -> (restype, argtypes)
 _F = ctypes.POINTER(c_float)
 PROTOTYPES = {
@@ -57,6 +67,10 @@ PROTOTYPES = {
     "nerf_b200_render_rays_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_merge_samples": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "nerf_b200_hierarchical_samples": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64,
+                                               c_void_p, c_void_p]),
+    "nerf_b200_composite_white": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "nerf_b200_ray_batch": (c_int, [_F, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_train_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nerf_b200_train_fwd_bwd": (c_int, [c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Params), c_void_p,
                                         c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_int,
@@ -64,6 +78,9 @@ PROTOTYPES = {
     "nerf_b200_train_fwd_bwd_ex": (c_int, [c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Params), c_void_p,
                                            c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_int,
                                            c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "nerf_b200_dp_bytes": (c_size_t, [c_int64]),
+    "nerf_b200_dp_reduce": (c_int, [ctypes.POINTER(DP), c_void_p]),
+    "nerf_b200_dp_adam_step": (c_int, [ctypes.POINTER(DP), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_launch_count": (c_uint64, []),
     "nerf_b200_set_watchdog_word": (None, [c_void_p]),
     "nerf_b200_set_trace_buffer": (None, [c_void_p]),

@@ -200,18 +200,32 @@ def merge_samples(z_sorted, z_new) -> torch.Tensor:
     return out
 
 
+def hierarchical_samples(weights, n_new: int, near: float = 2.0, far: float = 6.0, t_rand=None, u=None, seed: int = 0) -> torch.Tensor:
+    """Sorted union [R, S + n_new] of the coarse depths and the inverse-CDF samples drawn from ``weights`` [R,S] -- one
+    kernel (nerf_b200_hierarchical_samples).  ``u`` [R,n_new]: the uniforms (None: drawn in the kernel from ``seed``)."""
+    lib = L.load_library()
+    w = _dev(weights, "hierarchical_samples")
+    n, s = w.shape
+    tr = None if t_rand is None else _dev(t_rand, "hierarchical_samples")
+    uu = None if u is None else _dev(u, "hierarchical_samples")
+    if uu is not None and tuple(uu.shape) != (n, n_new):
+        raise ValueError("u must be [n_rays, n_new]")
+    out = torch.empty(n, s + n_new, device=w.device)
+    with torch.cuda.device(w.device):
+        L.check("nerf_b200_hierarchical_samples", lib.nerf_b200_hierarchical_samples(
+            _ptr(w), n, s, n_new, near, far, _ptr(tr), _ptr(uu), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _stream()))
+    return out
+
+
 def render_hierarchical(coarse_packed, fine_packed, rays_o, rays_d, n_coarse: int, n_importance: int,
-                        mode: int = L.BF16, near: float = 2.0, far: float = 6.0, u=None, t_rand=None):
+                        mode: int = L.BF16, near: float = 2.0, far: float = 6.0, u=None, t_rand=None, seed: int = 0):
     """Coarse pass -> inverse-CDF importance samples -> fine pass on the sorted union (BASELINE.json configs[4]:
-    128 coarse + 128 importance).  ``u`` [R,n_importance] uniforms (drawn here when None).  Returns
+    128 coarse + 128 importance): three launches -- fused render (weights out), fused sampling, fused render.
+    ``u`` [R,n_importance] uniforms (None: drawn inside the sampling kernel from ``seed``).  Returns
     (rgb_fine, depth_fine, rgb_coarse, z_union)."""
     ro, rd = _dev(rays_o, "render_hierarchical"), _dev(rays_d, "render_hierarchical")
     rgb_c, _, wts = render_rays(coarse_packed, ro, rd, n_coarse, mode, near, far, t_rand, want_weights=True)
-    _, z_c = sample_points(ro, rd, n_coarse, near, far, t_rand)
-    if u is None:
-        u = torch.rand(ro.shape[0], n_importance, device=ro.device)
-    _, z_new, _ = importance_sample(ro, rd, z_c, wts, u)
-    z_all = merge_samples(z_c, z_new)
+    z_all = hierarchical_samples(wts, n_importance, near, far, t_rand, u, seed)
     rgb_f, depth_f = render_rays(fine_packed, ro, rd, n_coarse + n_importance, mode, near, far, z_vals=z_all)
     return rgb_f, depth_f, rgb_c, z_all
 
@@ -227,7 +241,7 @@ class TrainPass:
 
     def __init__(self, model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_rays_global: Optional[int] = None,
                  near: float = 2.0, far: float = 6.0, mode: int = L.FP32, want_rgb: bool = True, slot: int = 0, packed=None,
-                 grad_out: Optional[dict] = None):
+                 grad_out: Optional[dict] = None, loss_sum: Optional[torch.Tensor] = None):
         """``model``: an ``nn.Module`` with the reference's parameter names (gradients accumulate into ``p.grad``), or
         a name -> tensor dict together with ``grad_out`` (name -> tensor the gradients accumulate into)."""
         self.lib = L.load_library()
@@ -259,7 +273,9 @@ class TrainPass:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _workspaces[(dev, slot)] = ws
         self.ws = ws
-        self.loss_sum = torch.zeros(1, device=dev)
+        # the kernels ACCUMULATE the sum of squared errors here: a caller-provided slot (e.g. the tail of a gradient
+        # bucket, so that the loss rides the gradient exchange) or a fresh zero
+        self.loss_sum = torch.zeros(1, device=dev) if loss_sum is None else loss_sum
         self.rgb = torch.empty(self.n, 3, device=dev) if want_rgb else None
         self.tr = None if t_rand is None else _dev(t_rand, "train_fwd_bwd")
         self.ps, self.gs = params_struct(params), params_struct(grads)
@@ -288,6 +304,43 @@ def train_fwd_bwd(model, rays_o, rays_d, target, n_samples: int, t_rand=None, n_
     (loss_term as a 0-dim tensor computed over this call's rays with the global normaliser, rgb [R,3])."""
     tp = TrainPass(model, rays_o, rays_d, target, n_samples, t_rand, n_rays_global, near, far, mode, want_rgb).run()
     return tp.loss, tp.rgb
+
+
+def composite_white(rgba: torch.Tensor) -> torch.Tensor:
+    """[..., 4] uint8 RGBA (CUDA) -> [..., 3] fp32 RGB on a white background, the reference loader's float64 arithmetic
+    (src/data/loader.py:46-54) bit for bit."""
+    lib = L.load_library()
+    if not rgba.is_cuda or rgba.dtype != torch.uint8 or rgba.shape[-1] != 4:
+        raise L.NerfB200Error("composite_white", -101, "expected a CUDA uint8 tensor [..., 4] (nerf_dbr_b200 has no CPU path)")
+    rgba = rgba.contiguous()
+    out = torch.empty(*rgba.shape[:-1], 3, device=rgba.device)
+    if rgba.numel():
+        with torch.cuda.device(rgba.device):
+            L.check("nerf_b200_composite_white", lib.nerf_b200_composite_white(_ptr(rgba), rgba.numel() // 4, _ptr(out), _stream()))
+    return out
+
+
+def ray_batch(pose: torch.Tensor, width: int, height: int, focal: float, pixel_index: torch.Tensor,
+              image: Optional[torch.Tensor] = None):
+    """(rays_o [n,3], rays_d [n,3], target [n,3] or None) for the selected pixels: the bits of
+    ``_get_rays(pose)[index]`` and ``image.reshape(-1, 3)[index]`` (trainer.py:100-118) without the full-image tensors."""
+    lib = L.load_library()
+    if not pixel_index.is_cuda or pixel_index.dtype != torch.int64:
+        raise L.NerfB200Error("ray_batch", -101, "pixel_index must be a CUDA int64 tensor (nerf_dbr_b200 has no CPU path)")
+    idx = pixel_index.contiguous()
+    n, dev = idx.numel(), idx.device
+    ro, rd = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+    tg = None
+    if image is not None:
+        image = _dev(image, "ray_batch")
+        if image.numel() != width * height * 3:
+            raise ValueError("image must hold height * width * 3 values")
+        tg = torch.empty(n, 3, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            L.check("nerf_b200_ray_batch", lib.nerf_b200_ray_batch(_c2w(pose), width, height, focal, _ptr(idx), n, _ptr(image),
+                                                                   _ptr(ro), _ptr(rd), _ptr(tg), _stream()))
+    return ro, rd, tg
 
 
 def launch_count() -> int:
