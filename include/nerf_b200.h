@@ -82,6 +82,12 @@ NERF_B200_API const char *nerf_b200_error_string(int code);
  * kernel streams with bulk async copies. */
 NERF_B200_API size_t nerf_b200_packed_bytes(void);
 NERF_B200_API int nerf_b200_pack_weights(const nerf_b200_params *params_host, void *packed, void *stream);
+/* pack_weights_ex: the same, writing only the parts a caller's modes read (a training loop re-packs every step).  The
+ * bf16 operand stream, the biases and the head weights are always written; `what` adds the fp32 K-major matrices
+ * (FP32 mode), the low-order bf16 stream (BF16X3) and the transposed stream of the backward chain (BF16 training).
+ * Parts not selected keep whatever the buffer held. */
+enum { NERF_B200_PACK_FP32_MATRICES = 1, NERF_B200_PACK_BF16_LO = 2, NERF_B200_PACK_DGRAD = 4, NERF_B200_PACK_ALL = 7 };
+NERF_B200_API int nerf_b200_pack_weights_ex(const nerf_b200_params *params_host, void *packed, int what, void *stream);
 
 /* ---- rays and samples ------------------------------------------------------------------
  * generate_rays: BaseUnifiedRenderer.generate_rays (base_renderer.py:223-258; also
@@ -257,7 +263,7 @@ NERF_B200_API int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200
  * several "ranks" whose allocations live on one GPU are run as reduce(0..W-1) then adam_step(0..W-1) on one stream. */
 #define NERF_B200_DP_MAX_WORLD 16
 #define NERF_B200_DP_CTL_BYTES 1024
-#define NERF_B200_DP_STATE_BYTES 1024
+#define NERF_B200_DP_STATE_BYTES 2048
 #define NERF_B200_DP_STATE_OPT_STEP 12
 typedef struct nerf_b200_dp {
     int rank, world;

@@ -12,7 +12,8 @@ from .host.b200_renderer import B200Renderer  # noqa: F401
 from .host.trainer import B200TrainStep, load_checkpoint, save_checkpoint  # noqa: F401
 from .host.b200_trainer import B200Trainer  # noqa: F401
 from .host.engine import TrainEngine  # noqa: F401
+from .host.data import SyntheticDataset, load_synthetic_data, write_standin_dataset  # noqa: F401
 from .host.autograd import render_rays_autograd  # noqa: F401
 
-__all__ = ["B200Renderer", "B200Trainer", "B200TrainStep", "TrainEngine", "save_checkpoint", "load_checkpoint", "render_rays_autograd", "BaseUnifiedRenderer", "SharedNeRFModel", "NeRFModel", "PositionalEncoding",
+__all__ = ["B200Renderer", "B200Trainer", "B200TrainStep", "TrainEngine", "SyntheticDataset", "load_synthetic_data", "write_standin_dataset", "save_checkpoint", "load_checkpoint", "render_rays_autograd", "BaseUnifiedRenderer", "SharedNeRFModel", "NeRFModel", "PositionalEncoding",
            "NerfB200Error", "build_library", "load_library"]

@@ -31,7 +31,7 @@ namespace opt {
 
 constexpr int kMaxWorld = NERF_B200_DP_MAX_WORLD;
 constexpr int kThreads = 256;
-constexpr int kMaxBlocksA = 128;
+constexpr int kMaxBlocksA = 256;
 constexpr long long kSpinLimit = 40000000000LL;           // ~20 s of SM clocks: a rank that never arrives is a dead job
 
 // ctl block at the head of the symmetric allocation (1024 bytes)
@@ -41,12 +41,13 @@ struct Ctl {
     float norm_part[kMaxWorld];                           // sum of squares of rank q's shard of the summed gradient
 };
 static_assert(sizeof(Ctl) <= NERF_B200_DP_CTL_BYTES, "ctl block");
+static_assert(kMaxBlocksA <= kThreads, "the last block fetches one partial per thread");
 
 struct Local {                                            // per-rank private state (device memory, zeroed by the caller)
     unsigned int step;                                    // steps completed: the flags carry step + 1
     unsigned int ticket_a, ticket_b;
     unsigned int opt_step;                                // optimizer steps taken (Adam's `step`, the scheduler's last_epoch): host-settable on resume
-    float block_part[kMaxBlocksA];
+    float block_part[kMaxBlocksA];                        // (the state block is NERF_B200_DP_STATE_BYTES)
 };
 static_assert(sizeof(Local) <= NERF_B200_DP_STATE_BYTES && offsetof(Local, opt_step) == NERF_B200_DP_STATE_OPT_STEP, "state block");
 
@@ -149,27 +150,44 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_kernel(const __grid_consta
     }
     const long long shard4 = a.n / 4 / a.world, first4 = shard4 * a.rank;          // float4 units
     float sq = 0.f;
-    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < shard4; i += (long long)gridDim.x * kThreads) {
-        const long long e = (first4 + i) * 4;
-        float4 s;
-        if (a.mc) {
-            s = multimem_ld_reduce_v4(g_of(a.mc) + e);                              // the switch sums the replicas
-        } else {
-            s = ld_sys_v4(g_of(a.peer[0]) + e);
+    constexpr int kBatch = 4;                             // independent 16-byte loads in flight per thread and peer
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i0 = blockIdx.x * (long long)kThreads + threadIdx.x; i0 < shard4; i0 += stride * kBatch) {
+        float4 s[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const long long i = i0 + b * stride;
+            s[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < shard4) s[b] = a.mc ? multimem_ld_reduce_v4(g_of(a.mc) + (first4 + i) * 4)      // the switch sums the replicas
+                                        : ld_sys_v4(g_of(a.peer[0]) + (first4 + i) * 4);
+        }
+        if (!a.mc)
             for (int q = 1; q < a.world; ++q) {                                     // rank order: same bits on every rank
-                const float4 t = ld_sys_v4(g_of(a.peer[q]) + e);
-                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+                float4 t[kBatch];
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const long long i = i0 + b * stride;
+                    t[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < shard4) t[b] = ld_sys_v4(g_of(a.peer[q]) + (first4 + i) * 4);
+                }
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) { s[b].x += t[b].x; s[b].y += t[b].y; s[b].z += t[b].z; s[b].w += t[b].w; }
             }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const long long i = i0 + b * stride;
+            if (i >= shard4) continue;
+            const long long e = (first4 + i) * 4;
+            if (a.mc) {
+                multimem_st_v4(gsum_of(a.mc, a.n) + e, s[b]);                       // one store, delivered to every replica
+            } else {
+                for (int q = 0; q < a.world; ++q) st_sys_v4(gsum_of(a.peer[q], a.n) + e, s[b]);
+            }
+            if (e + 0 < a.n_opt) sq = fmaf(s[b].x, s[b].x, sq);
+            if (e + 1 < a.n_opt) sq = fmaf(s[b].y, s[b].y, sq);
+            if (e + 2 < a.n_opt) sq = fmaf(s[b].z, s[b].z, sq);
+            if (e + 3 < a.n_opt) sq = fmaf(s[b].w, s[b].w, sq);
         }
-        if (a.mc) {
-            multimem_st_v4(gsum_of(a.mc, a.n) + e, s);                              // one store, delivered to every replica
-        } else {
-            for (int q = 0; q < a.world; ++q) st_sys_v4(gsum_of(a.peer[q], a.n) + e, s);
-        }
-        if (e + 0 < a.n_opt) sq = fmaf(s.x, s.x, sq);
-        if (e + 1 < a.n_opt) sq = fmaf(s.y, s.y, sq);
-        if (e + 2 < a.n_opt) sq = fmaf(s.z, s.z, sq);
-        if (e + 3 < a.n_opt) sq = fmaf(s.w, s.w, sq);
     }
     const float bs = block_sum(sq);
     __shared__ bool last;
@@ -182,11 +200,15 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_kernel(const __grid_consta
     }
     __syncthreads();
     if (!last) return;
-    // last block: the shard's sum of squares in block order, then publish it and signal "shard delivered"
+    // last block: the shard's sum of squares in block order (partials fetched in parallel, added by one thread), then
+    // publish it and signal "shard delivered"
+    __shared__ float parts[kMaxBlocksA];
+    __threadfence();
+    if (threadIdx.x < gridDim.x) parts[threadIdx.x] = *reinterpret_cast<volatile float *>(&a.local->block_part[threadIdx.x]);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
         float tot = 0.f;
-        for (unsigned int b = 0; b < gridDim.x; ++b) tot += *reinterpret_cast<volatile float *>(&a.local->block_part[b]);
+        for (unsigned int b = 0; b < gridDim.x; ++b) tot += parts[b];
         a.local->ticket_a = 0;
         for (int q = 0; q < a.world; ++q)
             *reinterpret_cast<volatile float *>(&ctl_of(a.peer[q])->norm_part[a.rank]) = tot;
@@ -295,7 +317,7 @@ int nerf_b200_dp_reduce(const nerf_b200_dp *dp, void *stream)
     int rc = opt::fill(a, dp);
     if (rc) return rc;
     const long long shard4 = a.n / 4 / a.world;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(opt::kMaxBlocksA, (shard4 + opt::kThreads * 2 - 1) / (opt::kThreads * 2)));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(opt::kMaxBlocksA, (shard4 + opt::kThreads * 4 - 1) / (opt::kThreads * 4)));
     opt::dp_reduce_kernel<<<grid, opt::kThreads, 0, (cudaStream_t)stream>>>(a);
     return launch_status();
 }

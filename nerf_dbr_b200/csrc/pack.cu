@@ -22,14 +22,18 @@ __device__ __forceinline__ ChunkSrc chunk_source(const nerf_b200_params &p, int 
     return {p.layer_w[c.layer], 256, n0, 64 * c.asrc, 64, 128, nullptr};
 }
 
-__global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ packed)
+__global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ packed, int what)
 {
     float *f = reinterpret_cast<float *>(packed);
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
 
-    // ---- fp32 region ----
-    for (size_t i = tid; i < F_END; i += nth) {
+    // ---- fp32 region ----  (without PACK_FP32_MATRICES: only what the tensor-core kernels read -- biases, head weights
+    // [0, F_W0T) and colour layer 0's direction block [F_WC0D, F_WO))
+    const bool mats = (what & NERF_B200_PACK_FP32_MATRICES) != 0;
+    const size_t lean = F_W0T + (F_WO - F_WC0D);
+    for (size_t ii = tid; ii < (mats ? F_END : lean); ii += nth) {
+        const size_t i = mats ? ii : (ii < F_W0T ? ii : F_WC0D + (ii - F_W0T));
         float v = 0.f;
         if (i < F_WSIG) { int l = (int)(i / 256), n = (int)(i % 256); v = p.layer_b[l][n]; }
         else if (i < F_BSIG) v = p.density_w[i - F_WSIG];
@@ -80,11 +84,11 @@ __global__ void pack_kernel(nerf_b200_params p, unsigned char *__restrict__ pack
         }
         size_t off = chunk_offset(ci) + swz128((uint32_t)n, (uint32_t)unit * 8);
         *reinterpret_cast<uint4 *>(packed + B_OFFSET + off) = *reinterpret_cast<const uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
+        if (what & NERF_B200_PACK_BF16_LO) *reinterpret_cast<uint4 *>(packed + B_LO_OFFSET + off) = *reinterpret_cast<const uint4 *>(lo);
     }
 
     // ---- dgrad stream: chunk (g, half, kb), element (k, n) = W[64 kb + n][128 half + k] ----
-    const size_t dg_units = (size_t)kDgChunks * 128 * 8;
+    const size_t dg_units = (what & NERF_B200_PACK_DGRAD) ? (size_t)kDgChunks * 128 * 8 : 0;
     for (size_t uidx = tid; uidx < dg_units; uidx += nth) {
         const int ci = (int)(uidx / 1024), k = (int)((uidx % 1024) / 8), unit = (int)(uidx % 8);
         const ChunkInfo c = kPackDgTable.c[ci];
@@ -118,14 +122,19 @@ size_t nerf_b200_packed_bytes(void) { return PACKED_BYTES; }
 
 int nerf_b200_pack_weights(const nerf_b200_params *params_host, void *packed, void *stream)
 {
-    if (!params_host || !packed) return NERF_B200_EINVAL;
+    return nerf_b200_pack_weights_ex(params_host, packed, NERF_B200_PACK_ALL, stream);
+}
+
+int nerf_b200_pack_weights_ex(const nerf_b200_params *params_host, void *packed, int what, void *stream)
+{
+    if (!params_host || !packed || (what & ~NERF_B200_PACK_ALL)) return NERF_B200_EINVAL;
     const nerf_b200_params &p = *params_host;
     for (int l = 0; l < 8; ++l)
         if (!p.layer_w[l] || !p.layer_b[l]) return NERF_B200_EINVAL;
     if (!p.density_w || !p.density_b || !p.color0_w || !p.color0_b || !p.color1_w || !p.color1_b)
         return NERF_B200_EINVAL;
     if ((uintptr_t)packed & 1023) return NERF_B200_EALIGN;
-    pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<unsigned char *>(packed));
+    pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p, reinterpret_cast<unsigned char *>(packed), what);
     return launch_status();
 }
 

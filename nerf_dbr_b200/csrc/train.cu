@@ -31,7 +31,8 @@ constexpr int kChunkSamples = 524288;        // samples per chunk (multiple of 6
 int tc_train_forward(const void *packed, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
                      float far, const float *t_rand, float *ws, int ws_ch, unsigned int *dbg, int sm_limit, cudaStream_t stream);
 int dgrad_chain_tc(const void *packed, float *ws, int ch, int n_samples, unsigned int *dbg, int sm_limit, cudaStream_t stream);
-int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias, int sm_limit,
+size_t wgrad_skinny_scratch_bytes();
+int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld, float *dbias, float *scratch, int sm_limit,
                  cudaStream_t stream);
 size_t wgrad_tc_scratch_bytes(int splits);
 int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_jobs, float *scratch, int ctas, cudaStream_t stream);
@@ -403,7 +404,7 @@ size_t nerf_b200_train_workspace_bytes(int n_rays, int n_samples)
     if (n_rays <= 0 || n_samples <= 0) return 0;
     long long per = (long long)std::min(n_rays, chunk_rays(n_samples)) * n_samples;
     long long ch = (per + 63) / 64 * 64;
-    return (size_t)ch * R_TOTAL * sizeof(float) + wgrad_tc_scratch_bytes(256);                // partials of one batched wgrad launch
+    return (size_t)ch * R_TOTAL * sizeof(float) + wgrad_tc_scratch_bytes(256) + 2 * wgrad_skinny_scratch_bytes();   // partials of one batched wgrad launch + the two skinny jobs
 }
 
 int nerf_b200_train_fwd_bwd(const void *packed, const nerf_b200_params *params, const nerf_b200_params *grads,
@@ -513,9 +514,11 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
                 // the big operand rows live in bf16 blocks (train_layout.h: G_* feature numbering)
                 const __nv_bfloat16 *wsb = reinterpret_cast<const __nv_bfloat16 *>(ws);
                 const int row_a = big_feature((int)((A - ws) / ch)), row_b = big_feature((int)((B - ws) / ch));
-                if (rows_a <= 4)
+                if (rows_a <= 4) {                   // density head (1 row), colour layer 1 (3 rows): own partial areas
+                    float *sk = scratch + wgrad_tc_scratch_bytes(256) / sizeof(float) + (size_t)(rows_a == 1 ? 0 : 1) * (wgrad_skinny_scratch_bytes() / sizeof(float));
                     return wgrad_skinny(A, rows_a, (int)ch, wsb, row_b, rows_b, const_cast<float *>(dW), ld, const_cast<float *>(db),
-                                        sm_limit, wst->s[1]);
+                                        sk, sm_limit, wst->s[1]);
+                }
                 jobs[n_jobs++] = WgradJob{row_a, rows_a, row_b, rows_b, const_cast<float *>(dW), ld, col_off, const_cast<float *>(db)};
                 return 0;
             }

@@ -45,7 +45,7 @@ struct Job {
     int row_b, rows_b;                           // B features, staged in whole blocks of 64, <= 256
     int n_b;                                     // MMA N: the valid B features rounded up to 16 (pad features hold zeros)
     float *partial;                              // [splits][rows_a][n_b]
-    float *dbias;                                // optional: dbias[n] += sum_s A[n][s]
+    float *bias_partial;                         // optional: [splits][rows_a] row sums of A over this CTA's slabs
 };
 struct Args {
     const __nv_bfloat16 *ws;                     // bf16 operand blocks
@@ -61,6 +61,9 @@ struct ReduceArgs {                              // block b reduces 64 elements 
     const float *partial[kMaxJobs];
     int splits[kMaxJobs], rows_a[kMaxJobs], n_b[kMaxJobs], rows_b_valid[kMaxJobs];
     float *dW[kMaxJobs];
+    const float *bias_partial[kMaxJobs];         // [splits][rows_a] or nullptr
+    float *dbias[kMaxJobs];
+    int bias_blk[kMaxJobs];                      // first of the job's bias blocks (one per 256 rows), after its element blocks
     int ld[kMaxJobs], col_off[kMaxJobs];
 };
 
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int per = (args.n_slabs + splits - 1) / splits;
     const int c_begin = split * per, c_end = min(args.n_slabs, c_begin + per);
     const int my_slabs = max(0, c_end - c_begin);
-    const bool want_bias = a.dbias != nullptr;
+    const bool want_bias = a.bias_partial != nullptr;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(bar(B_FULL + i), 1); mbar_init(bar(B_EMPTY + i), want_bias ? 9 : 1); }
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_EMPTY + s));
             }
-            if (t < a.rows_a && bs != 0.f) atomicAdd(a.dbias + t, bs);
+            if (t < a.rows_a) a.bias_partial[(size_t)split * a.rows_a + t] = bs;      // folded in CTA order by the reduce kernel
         }
         // ---------------- epilogue: accumulators -> this CTA's partial
         if (my_slabs > 0) {
@@ -177,46 +180,68 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<512>(tmem_base); }
 }
 
-// grads[n][col_off + k] += sum_split partial[split][n][k]   (k < rows_b_valid), every job of the chunk in one launch.
-// A block owns 64 consecutive elements of a job's [rows_a][n_b] partial; its four thread groups each take every
-// fourth split with four loads in flight (the partials were just written: they sit in L2, latency is the cost).
+// grads[n][col_off + k] += sum_split partial[split][n][k]   (k < rows_b_valid), dbias[n] += sum_split bias_partial[split][n]:
+// every job of the chunk in one launch, every sum in split order (no atomics: the result does not depend on timing).
+// A block owns 256 consecutive elements of a job's [rows_a][n_b] partial as 64 float4 (n_b is a multiple of 16, so a
+// float4 never straddles rows); its four thread groups each take every fourth split with four 16-byte loads in flight
+// (the partials were just written: they sit in L2, latency is the cost).  A job's bias blocks follow its element blocks.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceArgs r)
 {
-    __shared__ float part[4][64];
+    __shared__ float4 part[4][64];
     int j = 0;
     while (j + 1 < r.n_jobs && (int)blockIdx.x >= r.blk_begin[j + 1]) ++j;
     const int rows_a = r.rows_a[j], rows_b = r.n_b[j], splits = r.splits[j];
+    if (r.dbias[j] && (int)blockIdx.x >= r.bias_blk[j]) {
+        const int n = ((int)blockIdx.x - r.bias_blk[j]) * 256 + threadIdx.x;
+        if (n < rows_a) {
+            const float *p = r.bias_partial[j] + n;
+            float s = 0.f;
+#pragma unroll 4
+            for (int sp = 0; sp < splits; ++sp) s += __ldg(p + (size_t)sp * rows_a);
+            r.dbias[j][n] += s;
+        }
+        return;
+    }
     const int o = threadIdx.x & 63, sg = threadIdx.x >> 6;
-    const int i = (blockIdx.x - r.blk_begin[j]) * 64 + o, total = rows_a * rows_b;
+    const int i = ((blockIdx.x - r.blk_begin[j]) * 64 + o) * 4, total = rows_a * rows_b;
     const size_t stride = (size_t)rows_a * rows_b;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+    auto acc = [](float4 &d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
     if (i < total) {
         const float *p = r.partial[j] + i;
         int sp = sg;
         for (; sp + 12 < splits; sp += 16) {
-            s0 += __ldg(p + (size_t)sp * stride);
-            s1 += __ldg(p + (size_t)(sp + 4) * stride);
-            s2 += __ldg(p + (size_t)(sp + 8) * stride);
-            s3 += __ldg(p + (size_t)(sp + 12) * stride);
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p + (size_t)sp * stride));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p + (size_t)(sp + 4) * stride));
+            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p + (size_t)(sp + 8) * stride));
+            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p + (size_t)(sp + 12) * stride));
+            acc(s0, v0); acc(s1, v1); acc(s2, v2); acc(s3, v3);
         }
-        for (; sp < splits; sp += 4) s0 += __ldg(p + (size_t)sp * stride);
+        for (; sp < splits; sp += 4) acc(s0, __ldg(reinterpret_cast<const float4 *>(p + (size_t)sp * stride)));
     }
-    part[sg][o] = (s0 + s1) + (s2 + s3);
+    part[sg][o] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z),
+                              (s0.w + s1.w) + (s2.w + s3.w));
     __syncthreads();
     if (sg == 0 && i < total) {
         const int n = i / rows_b, k = i % rows_b;
-        if (k < r.rows_b_valid[j]) r.dW[j][(size_t)n * r.ld[j] + r.col_off[j] + k] += (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
+        const float4 a0 = part[0][o], a1 = part[1][o], a2 = part[2][o], a3 = part[3][o];
+        const float v[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                            (a0.w + a1.w) + (a2.w + a3.w)};
+        float *dst = r.dW[j] + (size_t)n * r.ld[j] + r.col_off[j] + k;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (k + e < r.rows_b_valid[j]) dst[e] += v[e];
     }
 }
 
 // Skinny weight gradients (density head: 1 output row; colour layer 1: 3): dW[a][k] += sum_s A[a][s] B[k][s],
 // dbias[a] += sum_s A[a][s].  A is fp32 [row][ch]; B is a group of bf16 operand blocks (train_layout.h).  A block
 // walks slabs: it stages the slab's contiguous B tile (coalesced 16-byte loads) and the 64 A values per row in
-// shared memory, thread k takes the dot products of B feature k, and the block's totals go out as one atomicAdd
-// per element.
+// shared memory, thread k takes the dot products of B feature k; the block's totals go to its row of `partial`
+// ([block][rows_a][rows_b + 1], last column = bias sums) and skinny_reduce_kernel folds the rows in block order.
 __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restrict__ A, int rows_a, int ch,
                                                            const __nv_bfloat16 *__restrict__ ws, int row_b, int rows_b,
-                                                           float *__restrict__ dW, int ld, float *__restrict__ dbias)
+                                                           float *__restrict__ partial)
 {
     __shared__ __align__(16) uint4 tile[256 * 8];          // [block][sample][64 features], swizzled as stored
     __shared__ __align__(16) float as[4][64];
@@ -241,36 +266,61 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float *__restri
                     if (r < rows_a) acc[r] = fmaf(as[r][s], b, acc[r]);
             }
         }
-        if (dbias && threadIdx.x >= 224 && threadIdx.x - 224 < rows_a) {   // bias: the last warp's first lanes
+        if (threadIdx.x >= 224 && threadIdx.x - 224 < rows_a) {   // bias: the last warp's first lanes
             const float *ar = as[threadIdx.x - 224];
 #pragma unroll 8
             for (int j = 0; j < 64; ++j) bs += ar[j];
         }
         __syncthreads();
     }
+    float *row = partial + (size_t)blockIdx.x * rows_a * (rows_b + 1);
     if (k < rows_b)
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            if (r < rows_a && acc[r] != 0.f) atomicAdd(dW + (size_t)r * ld + k, acc[r]);
-    if (dbias && threadIdx.x >= 224 && threadIdx.x - 224 < rows_a && bs != 0.f) atomicAdd(dbias + (threadIdx.x - 224), bs);
+            if (r < rows_a) row[r * (rows_b + 1) + k] = acc[r];
+    if (threadIdx.x >= 224 && threadIdx.x - 224 < rows_a) row[(threadIdx.x - 224) * (rows_b + 1) + rows_b] = bs;
+}
+
+// dW[a][k] += sum_block partial[block][a][k], dbias[a] += sum_block partial[block][a][rows_b].  One WARP per element:
+// lane l adds blocks l, l + 32, ... (independent loads), then a fixed shuffle tree -- the order never depends on timing.
+__global__ void __launch_bounds__(256) skinny_reduce_kernel(const float *__restrict__ partial, int blocks, int rows_a, int rows_b,
+                                                            float *__restrict__ dW, int ld, float *__restrict__ dbias)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, width = rows_b + 1, total = rows_a * width;
+    if (i >= total) return;
+    float s = 0.f;
+#pragma unroll 4
+    for (int b = lane; b < blocks; b += 32) s += __ldg(partial + (size_t)b * total + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane != 0) return;
+    const int r = i / width, k = i % width;
+    if (k < rows_b) dW[(size_t)r * ld + k] += s;
+    else if (dbias) dbias[r] += s;
 }
 
 }  // namespace wg
 
+constexpr int kSkinnyMaxBlocks = 1024;
+size_t wgrad_skinny_scratch_bytes() { return (size_t)kSkinnyMaxBlocks * 4 * 257 * sizeof(float); }
+
 int wgrad_skinny(const float *A, int rows_a, int ch, const __nv_bfloat16 *ws, int row_b, int rows_b, float *dW, int ld,
-                 float *dbias, int sm_limit, cudaStream_t stream)
+                 float *dbias, float *scratch, int sm_limit, cudaStream_t stream)
 {
-    if (rows_a > 4 || rows_b > 256 || (row_b & 63)) return NERF_B200_EINVAL;
+    if (rows_a > 4 || rows_b > 256 || (row_b & 63) || !scratch) return NERF_B200_EINVAL;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
-    const int grid = std::min(ch / 64, 4 * sms);
-    wg::wgrad_skinny_kernel<<<grid, 256, 0, stream>>>(A, rows_a, ch, ws, row_b, rows_b, dW, ld, dbias);
+    const int grid = std::max(1, std::min(std::min(ch / 64, 4 * sms), kSkinnyMaxBlocks));
+    wg::wgrad_skinny_kernel<<<grid, 256, 0, stream>>>(A, rows_a, ch, ws, row_b, rows_b, scratch);
+    int rc = launch_status();
+    if (rc) return rc;
+    wg::skinny_reduce_kernel<<<(rows_a * (rows_b + 1) + 7) / 8, 256, 0, stream>>>(scratch, grid, rows_a, rows_b, dW, ld, dbias);
     return launch_status();
 }
 
-size_t wgrad_tc_scratch_bytes(int ctas) { return (size_t)(ctas + wg::kMaxJobs) * 256 * 256 * sizeof(float); }
+size_t wgrad_tc_scratch_bytes(int ctas) { return (size_t)(ctas + wg::kMaxJobs) * (256 * 256 + 256) * sizeof(float); }   // element + bias partials
 
 // dW (+)= A-by-B^T over the chunk's samples on the tensor cores for every job in one launch, then one reduce launch.
 // A and B are feature groups (G_* numbering, starting on a block boundary) of the bf16 operand blocks at `ws`;
@@ -306,6 +356,8 @@ int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_
     }
     size_t off = 0;
     int blk = 0;
+    float *bias_base = scratch + (size_t)(ctas + wg::kMaxJobs) * 256 * 256;      // bias partials behind the element partials
+    size_t boff = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const WgradJob &q = jobs[j];
         wg::Job &d = a.job[j];
@@ -313,13 +365,16 @@ int wgrad_tc_batch(const __nv_bfloat16 *ws, int ch, const WgradJob *jobs, int n_
         d.rows_b = (q.rows_b_valid + 63) / 64 * 64;
         d.n_b = (q.rows_b_valid + 15) / 16 * 16;
         d.partial = scratch + off;
-        d.dbias = q.dbias;
+        d.bias_partial = q.dbias ? bias_base + boff : nullptr;
         a.cta_begin[j] = j ? a.cta_begin[j - 1] + share[j - 1] : 0;
         r.blk_begin[j] = blk;
         r.partial[j] = d.partial; r.splits[j] = share[j]; r.rows_a[j] = q.rows_a; r.n_b[j] = d.n_b;
         r.rows_b_valid[j] = q.rows_b_valid; r.dW[j] = q.dW; r.ld[j] = q.ld; r.col_off[j] = q.col_off;
+        r.bias_partial[j] = d.bias_partial; r.dbias[j] = q.dbias;
         off += (size_t)share[j] * q.rows_a * d.n_b;
-        blk += (q.rows_a * d.n_b + 63) / 64;
+        blk += (q.rows_a * d.n_b + 255) / 256;
+        r.bias_blk[j] = blk;
+        if (q.dbias) { boff += (size_t)share[j] * q.rows_a; blk += (q.rows_a + 255) / 256; }
     }
     a.cta_begin[n_jobs] = a.cta_begin[n_jobs - 1] + share[n_jobs - 1];
     r.blk_begin[n_jobs] = blk;

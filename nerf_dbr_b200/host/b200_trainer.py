@@ -112,21 +112,21 @@ class B200Trainer:
         self.fine_model.train()
         image = batch["image"].to(self.device, torch.float32)
         height, width = image.shape[:2]
-        rays_o, rays_d = ops.generate_rays(batch["pose"], width, height, float(batch["focal"]), device=self.device)
-        rays_o, rays_d, target = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), image.reshape(-1, 3)
-        n_rays = min(int(self.config.get("n_rays", 1024)), rays_o.shape[0])
-        select = torch.randperm(rays_o.shape[0], device=self.device, generator=self._gen)[:n_rays]
+        n_pixels = height * width
+        n_rays = min(int(self.config.get("n_rays", 1024)), n_pixels)
+        select = torch.randperm(n_pixels, device=self.device, generator=self._gen)[:n_rays]
         t_rand = torch.rand(n_rays, self.n_coarse, device=self.device, generator=self._gen)
         rank, world = _dist()
         first, count = ray_shard(rank, world, n_rays)
-        sel = select[first:first + count]
+        # this rank's rays and target colours straight from the pixel indices (the bits of _get_rays(pose)[select] and
+        # image.reshape(-1, 3)[select], trainer.py:100-118, without the full-image ray tensors)
+        rays_o, rays_d, target = ops.ray_batch(batch["pose"], width, height, float(batch["focal"]), select[first:first + count], image)
         if self.fused_step:
             eng = self._engine_for(n_rays)
-            eng.step(rays_o[sel], rays_d[sel], target[sel], t_rand[first:first + count])
+            eng.step(rays_o, rays_d, target, t_rand[first:first + count])
             loss = eng.out[0].clone()
             return float(loss) if sync else loss
-        loss, _, _ = self.step_fn(rays_o[sel], rays_d[sel], target[sel], t_rand=t_rand[first:first + count].contiguous(),
-                                  n_rays_global=n_rays)
+        loss, _, _ = self.step_fn(rays_o, rays_d, target, t_rand=t_rand[first:first + count].contiguous(), n_rays_global=n_rays)
         if self.gradient_clipping is not None:
             torch.nn.utils.clip_grad_norm_(self.step_fn.parameters(), self.gradient_clipping)
         self.optimizer.step()

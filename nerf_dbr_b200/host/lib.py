@@ -10,10 +10,12 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 _CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "libnerf_b200.so")
+# NERF_B200_LIB: load another build of the same ABI instead (A/B measurements of one kernel change on one box)
+LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_PKG, "libnerf_b200.so")
 
 FP32, BF16, BF16X3 = 0, 1, 2
 TRAIN_ACTIVATIONS, TRAIN_WEIGHT_GRADS, TRAIN_ALL = 1, 2, 3      # nerf_b200_train_fwd_bwd_ex phases
+PACK_FP32_MATRICES, PACK_BF16_LO, PACK_DGRAD, PACK_ALL = 1, 2, 4, 7   # nerf_b200_pack_weights_ex parts
 
 _lib = None
 
@@ -34,7 +36,7 @@ class Params(ctypes.Structure):
                 ("color1_w", c_void_p), ("color1_b", c_void_p)]
 
 
-DP_MAX_WORLD, DP_CTL_BYTES, DP_STATE_BYTES, DP_STATE_OPT_STEP = 16, 1024, 1024, 12
+DP_MAX_WORLD, DP_CTL_BYTES, DP_STATE_BYTES, DP_STATE_OPT_STEP = 16, 1024, 2048, 12
 
 
 class DP(ctypes.Structure):
@@ -51,6 +53,7 @@ PROTOTYPES = {
     "nerf_b200_error_string": (ctypes.c_char_p, [c_int]),
     "nerf_b200_packed_bytes": (c_size_t, []),
     "nerf_b200_pack_weights": (c_int, [ctypes.POINTER(Params), c_void_p, c_void_p]),
+    "nerf_b200_pack_weights_ex": (c_int, [ctypes.POINTER(Params), c_void_p, c_int, c_void_p]),
     "nerf_b200_generate_rays": (c_int, [_F, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_sample_points": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
@@ -109,6 +112,8 @@ def load_library() -> ctypes.CDLL:
                             "(nvcc, sm_100a); nerf_dbr_b200 has no CPU fallback")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
+        if os.environ.get("NERF_B200_LIB") and not hasattr(lib, name):
+            continue                     # an older build loaded for an A/B run: its missing entry points stay unbound
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args

@@ -50,8 +50,9 @@ def params_struct(tensors: dict) -> L.Params:
 
 
 def pack_weights(model_or_state, device: Optional[torch.device] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Pack one network's 22 tensors (nn.Module or state dict) into the kernel layout."""
+                 out: Optional[torch.Tensor] = None, what: int = L.PACK_ALL) -> torch.Tensor:
+    """Pack one network's 22 tensors (nn.Module or state dict) into the kernel layout.  ``what``: the optional parts
+    (``L.PACK_*``; default all) -- a training loop that re-packs every step writes only what its mode reads."""
     lib = L.load_library()
     sd = model_or_state.state_dict() if hasattr(model_or_state, "state_dict") else model_or_state
     if device is None:
@@ -66,7 +67,7 @@ def pack_weights(model_or_state, device: Optional[torch.device] = None,
     view = out[off:off + nbytes]
     p = params_struct(keep)
     with torch.cuda.device(device):
-        L.check("nerf_b200_pack_weights", lib.nerf_b200_pack_weights(ctypes.byref(p), _ptr(view), _stream()))
+        L.check("nerf_b200_pack_weights_ex", lib.nerf_b200_pack_weights_ex(ctypes.byref(p), _ptr(view), what, _stream()))
     view._keepalive = (out, keep)      # the pack kernel is asynchronous
     return view
 

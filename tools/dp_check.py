@@ -55,6 +55,9 @@ def main():
         if ref is not None:
             ref.step(*b)
             ref_losses.append(ref.loss())
+    diff = None
+    if rank == 0:
+        diff = float((eng.P[:eng.layout.n_opt] - ref.P[:ref.layout.n_opt]).norm()) / float(ref.P[:ref.layout.n_opt].norm())
     # timing: steps on static inputs, events on this rank's stream, max over ranks
     for _ in range(5):
         eng.step()
@@ -69,7 +72,6 @@ def main():
     t = torch.tensor([e0.elapsed_time(e1) / 50], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        diff = float((eng.P[:eng.layout.n_opt] - ref.P[:ref.layout.n_opt]).norm()) / float(ref.P[:ref.layout.n_opt].norm())
         ok = identical and all(abs(a - b) <= 3e-3 * abs(b) for a, b in zip(losses, ref_losses)) and diff <= 1e-3
         print(json.dumps({"ok": bool(ok), "world": world, "transport": eng.transport, "graph": bool(eng.graph),
                           "replicas_bit_identical": bool(identical), "losses": losses, "single_replica_losses": ref_losses,
