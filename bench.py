@@ -418,6 +418,99 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_hierarchical(args):
+    """--workload hierarchical: BASELINE.json configs[4] -- 1600x1200, 128 coarse + 128 importance samples (inverse-CDF
+    fine pass on the 256-sample sorted union), a 64-view orbit, every view cut into row bands over the GPUs.  Three
+    launches per view and rank: fused coarse render (compositing weights out), fused sampling (coarse depths +
+    inverse CDF + sorted union; uniforms drawn in the kernel), fused fine render at explicit depths.  A step = one view.
+    The reference's importance_sample is dead code (src/utils/rendering.py:54-100 raises at :89), so there is no
+    reference arm for this workload; FLOPs: 1,055,744 per network query, 128 coarse + 256 fine queries per ray."""
+    import torch
+    import torch.distributed as dist
+    from nerf_dbr_b200.host import lib as L
+    from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host.parallel import row_band
+    from nerf_dbr_b200.host.synthetic import orbit_pose
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w, h, n_c, n_i, views = 1600, 1200, 128, 128, 64
+    mode = L.BF16 if args.precision == "bf16" else L.FP32
+    weights = lego_weights()
+    net = ops.pack_weights({k: v.to(dev) for k, v in weights.items()}, dev)
+    row0, n_rows = row_band(rank, world, h)
+    poses = [orbit_pose(i % views, views) for i in range(args.steps + args.warmup)]
+    marks = []
+
+    def view(i, timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
+        if timed:
+            ev[0].record()
+        ro, rd = ops.generate_rays(poses[i], w, h, row0=row0, n_rows=n_rows, device=dev)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        if timed:
+            ev[1].record()
+        rgb_c, _, wts = ops.render_rays(net, ro, rd, n_c, mode, want_weights=True)
+        if timed:
+            ev[2].record()
+        z_all = ops.hierarchical_samples(wts, n_i, seed=i)
+        if timed:
+            ev[3].record()
+        rgb_f, dep_f = ops.render_rays(net, ro, rd, n_c + n_i, mode, z_vals=z_all)
+        if timed:
+            ev[4].record()
+            marks.append(ev)
+        return rgb_f
+
+    for i in range(args.warmup):
+        view(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = ops.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    for k in range(args.steps):
+        out = view(args.warmup + k, True)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = ops.launch_count() - n0
+    stage = [sum(ev[j].elapsed_time(ev[j + 1]) for ev in marks) / args.steps for j in range(4)]
+    total = sum(ev[0].elapsed_time(ev[4]) for ev in marks)
+    t = torch.tensor([total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        pk = peaks()
+        flop_rank = FLOP_PER_SAMPLE * n_rows * w * (n_c + n_c + n_i)
+        mlp_ms = stage[1] + stage[3]
+        tfl = flop_rank / (mlp_ms * 1e-3) / 1e12
+        samp_bytes = n_rows * w * 4 * (n_c + n_c + n_i)            # weights in, union out (uniforms drawn in the kernel)
+        emit({"metric": "Mrays/s at 1600x1200, 128 coarse + 128 importance samples/ray (hierarchical)", "value": w * h / (ms * 1e-3) / 1e6,
+              "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if mode == L.BF16 else "f32",
+              "data": "synthetic",
+              "config": {"workload": "BASELINE.json configs[4]: 1600x1200, 128 coarse + 128 inverse-CDF samples, fine pass on the sorted "
+                                     "union of 256, 64-view orbit, row bands over the GPUs", "rows_per_gpu": n_rows,
+                         "ms_rank0": {"generate_rays": stage[0], "coarse_render": stage[1], "sampling": stage[2], "fine_render": stage[3]},
+                         "launches_per_view": launches / args.steps, "finite": bool(torch.isfinite(out).all()),
+                         "timing": "CUDA events per view on the launching stream, summed; max over ranks",
+                         "l2": "per-view working set (weights + union: 3 GB at N = 1) exceeds the 126 MB L2"},
+              "gpu_launches": int(launches), "clocks": clocks,
+              "roofline": {"bound": "tensor", "achieved": tfl, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tfl / pk["bf16_tflops"],
+                           "traffic": None, "kernel": "fused_render_kernel<SRC_RAYS> (coarse + fine passes)",
+                           "algorithmic_flop_per_view_rank0": flop_rank,
+                           "sampling_kernel": {"bound": "hbm", "algorithmic_bytes": samp_bytes, "ms": stage[2],
+                                               "achieved_gbs": samp_bytes / (stage[2] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                                               "frac": samp_bytes / (stage[2] * 1e-3) / 1e9 / pk["hbm_gbs"]}}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,6 +532,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "train":
         return run_train(args)
+    if args.workload == "hierarchical":
+        return run_hierarchical(args)
 
     import torch
     import torch.distributed as dist

@@ -50,4 +50,13 @@ wts = torch.rand(R, S, device=dev)
 out["importance_sample"] = (timed(lambda: ops.importance_sample(ro, rd, z, wts, u)), (12 + 24) * R * S + 24 * R)
 _, z_new, _ = ops.importance_sample(ro, rd, z, wts, u)
 out["merge_samples"] = (timed(lambda: ops.merge_samples(z, z_new)), 16 * R * S)
+# the fused sampling kernel of the hierarchical path: weights (+ uniforms) in, sorted union out
+out["hierarchical_samples_u_given"] = (timed(lambda: ops.hierarchical_samples(wts, S, u=u)), (4 + 4 + 8) * R * S)
+out["hierarchical_samples_philox"] = (timed(lambda: ops.hierarchical_samples(wts, S, seed=1)), (4 + 8) * R * S)
+# data path: RGBA8 -> fp32 RGB on white (100 images of 800x800), ray batch of 4096 pixels
+rgba = torch.randint(0, 256, (100, 800, 800, 4), dtype=torch.uint8, device=dev)
+out["composite_white"] = (timed(lambda: ops.composite_white(rgba)), 16 * rgba.numel() // 4)
+img = torch.rand(H, W, 3, device=dev)
+sel = torch.randperm(R, device=dev)[:4096]
+out["ray_batch_4096"] = (timed(lambda: ops.ray_batch(pose, W, H, 800.0, sel, img)), (8 + 12 + 36) * 4096)
 print(json.dumps({k: {"ms": round(ms, 4), "algorithmic_GB": round(b / 1e9, 3), "GB_per_s": round(b / ms / 1e6, 1)} for k, (ms, b) in out.items()}, indent=1))
