@@ -92,6 +92,24 @@ def test_argument_errors_return_codes_and_enqueue_nothing():
                                           L.BF16, fake, fake, null, L.TRAIN_ALL, -1, null) == EINVAL   # negative SM limit
     assert lib.nerf_b200_train_fwd_bwd_ex(fake, ctypes.byref(ps), ctypes.byref(ps), fake, fake, fake, 4, 64, 2.0, 6.0, null, 4,
                                           L.FP32, fake, fake, null, L.TRAIN_ACTIVATIONS, 0, null) == -2  # split phases: BF16 only
+    # round-2 entry points
+    assert lib.nerf_b200_pack_weights_ex(ctypes.byref(ps), fake, 8, null) == EINVAL                    # unknown part flag
+    assert lib.nerf_b200_hierarchical_samples(null, 4, 64, 8, 2.0, 6.0, null, null, 0, fake, null) == EINVAL
+    assert lib.nerf_b200_hierarchical_samples(fake, 4, 48, 8, 2.0, 6.0, null, null, 0, fake, null) == -2  # S % 32 != 0
+    assert lib.nerf_b200_hierarchical_samples(fake, 4, 64, 2048, 2.0, 6.0, null, null, 0, fake, null) == -2
+    assert lib.nerf_b200_composite_white(null, 16, fake, null) == EINVAL
+    assert lib.nerf_b200_composite_white(ctypes.c_void_p(0x1002), 16, fake, null) == -3                # RGBA pixels are 4-byte units
+    c2w = (ctypes.c_float * 16)(*([0.0] * 16))
+    assert lib.nerf_b200_ray_batch(c2w, 8, 8, 800.0, fake, 4, null, fake, fake, fake, null) == EINVAL   # target without an image
+    dp = L.DP()
+    dp.rank, dp.world, dp.n, dp.n_opt = 0, 2, 1026, 1000                                                # n not a multiple of 4 * world
+    dp.peer[0], dp.peer[1], dp.state = 0x1000, 0x2000, 0x3000
+    assert lib.nerf_b200_dp_reduce(ctypes.byref(dp), null) == EINVAL
+    dp.n, dp.rank = 1024, 2                                                                             # rank outside the world
+    assert lib.nerf_b200_dp_reduce(ctypes.byref(dp), null) == EINVAL
+    dp.rank, dp.peer[1] = 1, 0                                                                          # a peer mapping is missing
+    assert lib.nerf_b200_dp_adam_step(ctypes.byref(dp), fake, fake, fake, fake, null, null) == EINVAL
+    assert lib.nerf_b200_dp_bytes(1024) == L.DP_CTL_BYTES + 2 * 1024 * 4 and lib.nerf_b200_dp_bytes(0) == 0
     for code in (-1, -2, -3):
         assert lib.nerf_b200_error_string(code)
     assert lib.nerf_b200_launch_count() == launches
