@@ -171,6 +171,29 @@ NERF_B200_API int nerf_b200_render_rays_ex(const void *packed, const float *rays
 NERF_B200_API int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_rays, int n_sorted, int n_new,
                             float *z_out, void *stream);
 
+/* ---- FP8 mode (quantised weights and activations on the tensor cores) -----------------------------
+ * The B200 counterpart of the reference's CompressedNeRFRenderer (src/benchmark/compressed_renderer.py:89-211:
+ * per-tensor int8 weights dequantised to fp16 on the CPU): the fused render kernel with e4m3 operands for every
+ * 256-wide contraction (tcgen05.mma.kind::f8f6f4, twice the bf16 rate), bf16 for the encoded-position inputs, fp32
+ * accumulation, heads and compositing.  A lossy mode: judged against the compressed renderer, not against the 1e-4 /
+ * 0.05 dB gates.
+ *
+ * pack_weights_fp8: `packed` = the network's regular packed buffer (already filled by nerf_b200_pack_weights: the
+ * calibration pass runs the FP32 kernel on it), calib_positions / calib_directions [n_calib,3] = sample points of the
+ * scene (the activation scales are 2^floor(log2(240 / max)) of what the fp32 network produces on them),
+ * packed_fp8 = caller-owned device buffer of nerf_b200_packed_fp8_bytes() bytes, 1024-byte aligned.
+ * render_image_fp8 / render_rays_fp8: nerf_b200_render_image / nerf_b200_render_rays_ex on that buffer. */
+NERF_B200_API size_t nerf_b200_packed_fp8_bytes(void);
+NERF_B200_API int nerf_b200_pack_weights_fp8(const nerf_b200_params *params_host, const void *packed,
+                               const float *calib_positions, const float *calib_directions, int64_t n_calib,
+                               void *packed_fp8, void *stream);
+NERF_B200_API int nerf_b200_render_image_fp8(const void *packed_fp8, const float *c2w_host, int width, int height, float focal,
+                               float near, float far, int n_samples, int row0, int n_rows, float *rgb_out,
+                               float *depth_out, void *stream);
+NERF_B200_API int nerf_b200_render_rays_fp8(const void *packed_fp8, const float *rays_o, const float *rays_d, int n_rays,
+                              int n_samples, float near, float far, const float *t_rand, const float *z_vals,
+                              float *rgb_out, float *depth_out, float *acc_out, float *weights_out, void *stream);
+
 /* hierarchical_samples: the sampling side of a coarse -> importance -> fine render (BASELINE.json configs[4]) as ONE
  * kernel: VolumeRenderer.sample_points_on_rays (the coarse depths: uniform, or stratified with t_rand [n_rays,n_samples])
  * + VolumeRenderer.importance_sample (src/utils/rendering.py:54-100, with the shape fix; `weights` [n_rays,n_samples]

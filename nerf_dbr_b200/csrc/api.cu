@@ -8,6 +8,8 @@ int simt_render_rays(const void *, const float *, const float *, int, int, float
 int tc_render_pose(const void *, const float *, int, int, float, float, float, int, int, int, bool, float *, float *, unsigned int *, cudaStream_t);
 int tc_render_rays(const void *, const float *, const float *, int, int, float, float, const float *, const float *, bool, float *, float *, float *, float *, unsigned int *, cudaStream_t);
 int tc_query_points(const void *, const float *, const float *, long long, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_pose_fp8(const void *, const float *, int, int, float, float, float, int, int, int, float *, float *, unsigned int *, cudaStream_t);
+int tc_render_rays_fp8(const void *, const float *, const float *, int, int, float, float, const float *, const float *, float *, float *, float *, float *, unsigned int *, cudaStream_t);
 }
 using namespace nerfb200;
 
@@ -97,6 +99,27 @@ int nerf_b200_render_rays_ex(const void *packed, const float *rays_o, const floa
                               mode == NERF_B200_BF16X3, rgb_out, depth_out, acc_out, weights_out, watchdog_word(),
                               (cudaStream_t)stream);
     return NERF_B200_EINVAL;
+}
+
+int nerf_b200_render_image_fp8(const void *packed_fp8, const float *c2w_host, int width, int height, float focal, float near,
+                               float far, int n_samples, int row0, int n_rows, float *rgb_out, float *depth_out, void *stream)
+{
+    if (!packed_fp8 || !c2w_host || !rgb_out || !depth_out || width <= 0 || height <= 0 || n_samples <= 0 || n_rows <= 0 ||
+        row0 < 0 || row0 + n_rows > height || !(focal > 0.f))
+        return NERF_B200_EINVAL;
+    if ((uintptr_t)packed_fp8 & 1023) return NERF_B200_EALIGN;
+    return tc_render_pose_fp8(packed_fp8, c2w_host, width, height, focal, near, far, n_samples, row0, n_rows, rgb_out, depth_out,
+                              watchdog_word(), (cudaStream_t)stream);
+}
+
+int nerf_b200_render_rays_fp8(const void *packed_fp8, const float *rays_o, const float *rays_d, int n_rays, int n_samples,
+                              float near, float far, const float *t_rand, const float *z_vals, float *rgb_out, float *depth_out,
+                              float *acc_out, float *weights_out, void *stream)
+{
+    if (!packed_fp8 || !rays_o || !rays_d || !rgb_out || !depth_out || n_rays <= 0 || n_samples <= 0) return NERF_B200_EINVAL;
+    if ((uintptr_t)packed_fp8 & 1023) return NERF_B200_EALIGN;
+    return tc_render_rays_fp8(packed_fp8, rays_o, rays_d, n_rays, n_samples, near, far, t_rand, z_vals, rgb_out, depth_out, acc_out,
+                              weights_out, watchdog_word(), (cudaStream_t)stream);
 }
 
 int nerf_b200_render_rays(const void *packed, const float *rays_o, const float *rays_d, int n_rays,

@@ -23,6 +23,7 @@ struct SimtArgs {
     const float *positions, *directions;
     long long n_points;
     float *sigma_out, *rgb_out;
+    float *amax;                          // SRC_POINTS, optional: per-layer activation maxima (FP8 calibration)
     // SRC_RAYS / SRC_POSE
     Pose pose;
     int width, row0;
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(kSimtThreads, 1) simt_mlp_kernel(SimtArgs a)
             __syncthreads();
             simt_encode(sm, tid);
             float4 r;
-            simt_network(sm, a.wf, tid, r);
-            if (tid < TM) {
+            simt_network(sm, a.wf, tid, r, a.amax);
+            if (tid < TM && a.sigma_out) {
                 long long g = tile * TM + tid;
                 if (g < a.n_points) {
                     a.sigma_out[g] = r.x;
@@ -214,6 +215,17 @@ int simt_query(const void *packed, const float *positions, const float *directio
     a.wf = reinterpret_cast<const float *>(packed);
     a.positions = positions; a.directions = directions; a.n_points = n;
     a.sigma_out = sigma; a.rgb_out = rgb;
+    return simt_launch<SRC_POINTS>(a, (n + TM - 1) / TM, stream);
+}
+
+// FP8-mode calibration: run the fp32 network over `n` (position, direction) rows and keep the per-layer activation
+// maxima in amax[8] (device, zeroed by the caller).  Rows past n are zero-padded points: they only add small values.
+int simt_calibrate(const void *packed, const float *positions, const float *directions, long long n, float *amax, cudaStream_t stream)
+{
+    SimtArgs a = {};
+    a.wf = reinterpret_cast<const float *>(packed);
+    a.positions = positions; a.directions = directions; a.n_points = n;
+    a.amax = amax;
     return simt_launch<SRC_POINTS>(a, (n + TM - 1) / TM, stream);
 }
 

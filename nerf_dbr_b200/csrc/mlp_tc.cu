@@ -48,6 +48,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "train_layout.h"
+#include "fp8_layout.h"
 
 namespace nerfb200 {
 namespace tc {
@@ -974,6 +975,32 @@ static int launch(Args &a, cudaStream_t stream)
     return launch_status();
 }
 
+#include "mlp_tc_fp8.inl"
+
+template <int SRC>
+static int launch_fp8(Args &a, cudaStream_t stream)
+{
+    a.pair = cluster_default();
+    int grid = plan(a);
+    if (a.pair > 1 && a.n_tiles < 4 * grid) { a.pair = 1; grid = plan(a); }
+    if (grid < 0) return grid;
+    cudaError_t e = cudaFuncSetAttribute(fused_render_fp8_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    if (a.pair > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = a.pair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, fused_render_fp8_kernel<SRC>, a);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+        return launch_status();
+    }
+    fused_render_fp8_kernel<SRC><<<grid, kThreads, kSmemBytes, stream>>>(a);
+    return launch_status();
+}
+
 }  // namespace tc
 
 
@@ -1005,6 +1032,36 @@ int tc_render_rays(const void *packed, const float *rays_o, const float *rays_d,
     a.near = near; a.far = far;
     a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
     return split ? tc::launch<tc::SRC_RAYS, true>(a, stream) : tc::launch<tc::SRC_RAYS, false>(a, stream);
+}
+
+// FP8 mode (fp8_layout.h): `packed_fp8` = the buffer nerf_b200_pack_weights_fp8 filled
+int tc_render_pose_fp8(const void *packed_fp8, const float *c2w, int width, int height, float focal, float near, float far,
+                       int n_samples, int row0, int n_rows, float *rgb_out, float *depth_out, unsigned int *dbg, cudaStream_t stream)
+{
+    tc::Args a = {};
+    a.packed = reinterpret_cast<const unsigned char *>(packed_fp8);
+    a.pose = pose_from_c2w(c2w);
+    a.width = width; a.row0 = row0;
+    a.half_w = (float)((double)width * 0.5); a.half_h = (float)((double)height * 0.5); a.focal = focal;
+    a.n_rays = n_rows * width; a.n_samples = n_samples;
+    a.near = near; a.far = far;
+    a.rgb_map = rgb_out; a.depth = depth_out; a.acc = nullptr; a.dbg = dbg;
+    a.trace = trace_buffer();
+    return tc::launch_fp8<tc::SRC_POSE>(a, stream);
+}
+
+int tc_render_rays_fp8(const void *packed_fp8, const float *rays_o, const float *rays_d, int n_rays, int n_samples, float near,
+                       float far, const float *t_rand, const float *z_vals, float *rgb_out, float *depth_out, float *acc_out,
+                       float *weights_out, unsigned int *dbg, cudaStream_t stream)
+{
+    tc::Args a = {};
+    a.z_vals = z_vals; a.weights = weights_out;
+    a.packed = reinterpret_cast<const unsigned char *>(packed_fp8);
+    a.rays_o = rays_o; a.rays_d = rays_d; a.t_rand = t_rand;
+    a.n_rays = n_rays; a.n_samples = n_samples;
+    a.near = near; a.far = far;
+    a.rgb_map = rgb_out; a.depth = depth_out; a.acc = acc_out; a.dbg = dbg;
+    return tc::launch_fp8<tc::SRC_RAYS>(a, stream);
 }
 
 // NeRFModel.forward on (point, direction) rows: query_nerf_networks in BF16 mode

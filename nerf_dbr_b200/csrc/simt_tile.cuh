@@ -107,7 +107,24 @@ static __device__ void simt_encode(SimtSmem &sm, int tid)
 
 // The network on one 64-sample tile: sm.pe / sm.de -> (sigma, rgb) for row m < 64 returned to
 // thread tid == m (others return garbage).
-static __device__ void simt_network(SimtSmem &sm, const float *__restrict__ wf, int tid, float4 &result)
+// amax (optional, device float[8], calibration of the FP8 mode): amax[l] = max over everything seen of trunk layer l's
+// activations (non-negative floats order like their bit patterns, so an integer atomicMax does it)
+template <int CN>
+__device__ __forceinline__ void simt_track_max(const float (&acc)[8][CN], const float *__restrict__ bias, int n0, float *amax_l)
+{
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) {
+        const float b = __ldg(bias + n0 + j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, acc[i][j] + b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(amax_l), __float_as_int(mx));
+}
+
+static __device__ void simt_network(SimtSmem &sm, const float *__restrict__ wf, int tid, float4 &result, float *amax = nullptr)
 {
     const int m0 = (tid & 7) * 8, ng = tid >> 3;
     float acc[8][8];
@@ -116,6 +133,7 @@ static __device__ void simt_network(SimtSmem &sm, const float *__restrict__ wf, 
     zero_acc(acc);
     simt_accumulate<8>(acc, sm.pe, 64, wf + F_W0T, sm.ws, tid, m0, n0);
     simt_store_relu<8>(acc, wf + F_BIAS, sm.actA, m0, n0);
+    if (amax) simt_track_max<8>(acc, wf + F_BIAS, n0, amax);
     float *in = sm.actA, *out = sm.actB;
     for (int l = 1; l < 8; ++l) {
         zero_acc(acc);
@@ -123,6 +141,7 @@ static __device__ void simt_network(SimtSmem &sm, const float *__restrict__ wf, 
         if (l == 4) simt_accumulate<8>(acc, sm.pe, 64, wf + F_W4P, sm.ws, tid, m0, n0);
         // `out` was last read two layers ago; the __syncthreads inside accumulate order it
         simt_store_relu<8>(acc, wf + F_BIAS + l * 256, out, m0, n0);
+        if (amax) simt_track_max<8>(acc, wf + F_BIAS + l * 256, n0, amax + l);
         float *t = in; in = out; out = t;
     }
     // `in` = layer-7 activations h; colour layer 0 (N = 128) -> `out`

@@ -23,22 +23,24 @@ except Exception:  # standalone
 
 class B200Renderer(_Base):
     """precision = 'bf16' (tcgen05 tensor cores, the throughput mode), 'bf16x3' (tensor cores with split
-    operands: max-abs ~1e-5 against PyTorchCPURenderer at a third of the bf16 rate) or 'fp32' (CUDA-core
-    FFMA, max-abs ~2e-6)."""
+    operands: max-abs ~1e-5 against PyTorchCPURenderer at a third of the bf16 rate), 'fp32' (CUDA-core
+    FFMA, max-abs ~2e-6) or 'fp8' (e4m3 weights and activations on the tensor cores: the lossy, fastest mode -- this
+    renderer's answer to CompressedNeRFRenderer, src/benchmark/compressed_renderer.py)."""
 
     def __init__(self, precision: str = "bf16", device_index: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA not available on this system")
         L.load_library()                       # raises if the CUDA library was not built
-        modes = {"bf16": L.BF16, "bf16x3": L.BF16X3, "fp32": L.FP32}
+        modes = {"bf16": L.BF16, "bf16x3": L.BF16X3, "fp32": L.FP32, "fp8": L.FP8}
         if precision not in modes:
-            raise ValueError("precision must be 'bf16', 'bf16x3' or 'fp32'")
+            raise ValueError("precision must be 'bf16', 'bf16x3', 'fp32' or 'fp8'")
         self.precision = precision
         self.mode = modes[precision]
         self.device_index = device_index
         super().__init__(f"B200 {precision.upper()}", "cuda")
         self._torch_device = torch.device("cuda", device_index)
         self._packed = {}
+        self._packed_fp8 = {}
 
     # ---- setup: load the shared checkpoint, pack both networks once ---------------------------
     def setup(self, checkpoint_path: str):
@@ -46,11 +48,18 @@ class B200Renderer(_Base):
         coarse, fine = self.shared_model.get_models(self.device)
         self._packed = {"coarse": ops.pack_weights(coarse, self._torch_device),
                         "fine": ops.pack_weights(fine, self._torch_device)}
+        self._packed_fp8 = {}
+        if self.mode == L.FP8:                 # quantise once: scales calibrated on sample points of the benchmark orbit
+            calib = ops.calibration_points(near=self.near, far=self.far, device=self._torch_device)
+            self._packed_fp8 = {k: ops.pack_weights_fp8(m, self._torch_device, calib, self._packed[k])
+                                for k, m in (("coarse", coarse), ("fine", fine))}
 
-    def _net(self, use_fine: bool = True) -> torch.Tensor:
+    def _net(self, use_fine: bool = True, render: bool = False) -> torch.Tensor:
+        """The packed network; ``render=True`` in FP8 mode: the quantised buffer the fused render entry points take."""
         if not self._packed:
             raise RuntimeError("Models not loaded. Call setup() first.")
-        return self._packed["fine" if use_fine else "coarse"]
+        src = self._packed_fp8 if (render and self.mode == L.FP8) else self._packed
+        return src["fine" if use_fine else "coarse"]
 
     # ---- the reference interface -----------------------------------------------------------------
     def generate_rays(self, camera_pose, width: int, height: int, focal: float = 800.0):
@@ -65,9 +74,9 @@ class B200Renderer(_Base):
     def query_nerf_networks(self, positions, directions, use_fine: bool = True):
         """(density [N,1], rgb [N,3]) (base_renderer.py:165-188), one view direction per row.  'bf16': the fused
         tensor-core kernel's (point, direction) variant; 'fp32' and 'bf16x3' (no split-precision variant of this
-        entry point): the FP32 CUDA-core kernel."""
+        entry point): the FP32 CUDA-core kernel; 'fp8' (fused render entry points only): the BF16 kernel."""
         return ops.query_network(self._net(use_fine), positions.to(self._torch_device),
-                                 directions.to(self._torch_device), L.BF16 if self.mode == L.BF16 else L.FP32)
+                                 directions.to(self._torch_device), L.BF16 if self.mode in (L.BF16, L.FP8) else L.FP32)
 
     def execute_volume_rendering(self, densities, colors, z_vals, ray_directions) -> Tuple[torch.Tensor, torch.Tensor]:
         """(rgb_map [R,3], depth_map [R]) (pytorch_renderers.py:105-125)."""
@@ -79,7 +88,7 @@ class B200Renderer(_Base):
         """(rgb [H,W,3], depth [H,W]) device tensors: one fused kernel launch, fine network, uniform
         samples (pytorch_renderers.py:127-170)."""
         width, height = resolution
-        return ops.render_image(self._net(True), camera_pose, width, height, samples_per_ray, self.mode,
+        return ops.render_image(self._net(True, render=True), camera_pose, width, height, samples_per_ray, self.mode,
                                 800.0, self.near, self.far)
 
     def render_image_hierarchical(self, camera_pose, resolution: Tuple[int, int], n_coarse: int = 128,
@@ -89,7 +98,7 @@ class B200Renderer(_Base):
         on the sorted union.  Returns (rgb [H,W,3], depth [H,W])."""
         width, height = resolution
         ro, rd = self.generate_rays(camera_pose, width, height)
-        rgb, depth, _, _ = ops.render_hierarchical(self._net(False), self._net(True), ro.reshape(-1, 3), rd.reshape(-1, 3),
+        rgb, depth, _, _ = ops.render_hierarchical(self._net(False, render=True), self._net(True, render=True), ro.reshape(-1, 3), rd.reshape(-1, 3),
                                                    n_coarse, n_importance, self.mode, self.near, self.far, u)
         return rgb.reshape(height, width, 3), depth.reshape(height, width)
 
@@ -114,8 +123,8 @@ class B200Renderer(_Base):
                 b = sets[i & 1]
                 if i >= 2:
                     main.wait_event(b["copied"])                         # the device buffers of this set are free again
-                ops.render_image(self._net(True), pose, width, height, samples_per_ray, self.mode, 800.0, self.near, self.far,
-                                 row0, n_rows, b["rgb"], b["depth"])
+                ops.render_image(self._net(True, render=True), pose, width, height, samples_per_ray, self.mode, 800.0, self.near,
+                                 self.far, row0, n_rows, b["rgb"], b["depth"])
                 b["rendered"].record(main)
                 side.wait_event(b["rendered"])
                 with torch.cuda.stream(side):
@@ -134,5 +143,5 @@ class B200Renderer(_Base):
                     out_rgb=None, out_depth=None):
         """The multi-GPU shard: rows [row0, row0+n_rows) of the image."""
         width, height = resolution
-        return ops.render_image(self._net(True), camera_pose, width, height, samples_per_ray, self.mode,
+        return ops.render_image(self._net(True, render=True), camera_pose, width, height, samples_per_ray, self.mode,
                                 800.0, self.near, self.far, row0, n_rows, out_rgb, out_depth)

@@ -14,6 +14,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_PKG, "libnerf_b200.so")
 
 FP32, BF16, BF16X3 = 0, 1, 2
+FP8 = 3                         # host-side selector only: FP8 mode has its own entry points and weight buffer
 TRAIN_ACTIVATIONS, TRAIN_WEIGHT_GRADS, TRAIN_ALL = 1, 2, 3      # nerf_b200_train_fwd_bwd_ex phases
 PACK_FP32_MATRICES, PACK_BF16_LO, PACK_DGRAD, PACK_ALL = 1, 2, 4, 7   # nerf_b200_pack_weights_ex parts
 
@@ -70,6 +71,12 @@ PROTOTYPES = {
     "nerf_b200_render_rays_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_merge_samples": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "nerf_b200_packed_fp8_bytes": (c_size_t, []),
+    "nerf_b200_pack_weights_fp8": (c_int, [ctypes.POINTER(Params), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "nerf_b200_render_image_fp8": (c_int, [c_void_p, _F, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_void_p,
+                                           c_void_p, c_void_p]),
+    "nerf_b200_render_rays_fp8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerf_b200_hierarchical_samples": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64,
                                                c_void_p, c_void_p]),
     "nerf_b200_composite_white": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

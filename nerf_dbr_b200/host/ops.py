@@ -72,6 +72,50 @@ def pack_weights(model_or_state, device: Optional[torch.device] = None,
     return view
 
 
+def calibration_points(n_views: int = 4, width: int = 40, height: int = 30, n_samples: int = 32, near: float = 2.0,
+                       far: float = 6.0, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(positions, directions) [n,3] of sample points along the rays of a few orbit views: what the FP8 mode's
+    activation scales are calibrated on when the caller has no better sample of the scene."""
+    from .synthetic import orbit_pose
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    pos, dirs = [], []
+    for i in range(n_views):
+        ro, rd = generate_rays(orbit_pose(i, n_views), width, height, device=device)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        pts, _ = sample_points(ro, rd, n_samples, near, far)
+        pos.append(pts.reshape(-1, 3))
+        dirs.append(rd[:, None, :].expand(-1, n_samples, -1).reshape(-1, 3))
+    return torch.cat(pos).contiguous(), torch.cat(dirs).contiguous()
+
+
+def pack_weights_fp8(model_or_state, device: Optional[torch.device] = None, calib=None, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Quantise one network for FP8 mode (nerf_b200_pack_weights_fp8): e4m3 weights with per-row power-of-two scales,
+    activation scales calibrated by running the fp32 network on ``calib`` = (positions, directions) [n,3] (default:
+    ``calibration_points``).  Returns the 1024-aligned FP8 buffer (its fp32 head holds the scales, fp8_layout.h)."""
+    lib = L.load_library()
+    sd = model_or_state.state_dict() if hasattr(model_or_state, "state_dict") else model_or_state
+    if device is None:
+        device = next(iter(sd.values())).device
+        if device.type != "cuda":
+            device = torch.device("cuda", torch.cuda.current_device())
+    keep = {k: sd[k].detach().to(device, torch.float32).contiguous() for k in STATE_ORDER}
+    if packed is None:
+        packed = pack_weights(keep, device)
+    if calib is None:
+        calib = calibration_points(device=device)
+    pos, dirs = _dev(calib[0], "pack_weights_fp8"), _dev(calib[1], "pack_weights_fp8")
+    nbytes = lib.nerf_b200_packed_fp8_bytes()
+    buf = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    view = buf[off:off + nbytes]
+    p = params_struct(keep)
+    with torch.cuda.device(device):
+        L.check("nerf_b200_pack_weights_fp8", lib.nerf_b200_pack_weights_fp8(ctypes.byref(p), _ptr(packed), _ptr(pos), _ptr(dirs),
+                                                                             pos.shape[0], _ptr(view), _stream()))
+    view._keepalive = (buf, keep, packed, pos, dirs)
+    return view
+
+
 def generate_rays(pose: torch.Tensor, width: int, height: int, focal: float = 800.0, row0: int = 0,
                   n_rows: Optional[int] = None, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = L.load_library()
@@ -161,6 +205,10 @@ def render_image(packed: torch.Tensor, pose: torch.Tensor, width: int, height: i
     rgb = out_rgb if out_rgb is not None else torch.empty(n_rows, width, 3, device=dev)
     depth = out_depth if out_depth is not None else torch.empty(n_rows, width, device=dev)
     with torch.cuda.device(dev):
+        if mode == L.FP8:                            # `packed` is the FP8 buffer (pack_weights_fp8)
+            L.check("nerf_b200_render_image_fp8", lib.nerf_b200_render_image_fp8(
+                _ptr(packed), _c2w(pose), width, height, focal, near, far, n_samples, row0, n_rows, _ptr(rgb), _ptr(depth), _stream()))
+            return rgb, depth
         L.check("nerf_b200_render_image", lib.nerf_b200_render_image(
             _ptr(packed), _c2w(pose), width, height, focal, near, far, n_samples, row0, n_rows, mode,
             _ptr(rgb), _ptr(depth), _stream()))
@@ -184,9 +232,14 @@ def render_rays(packed: torch.Tensor, rays_o, rays_d, n_samples: int, mode: int 
         raise ValueError("z_vals must be [n_rays, n_samples]")
     wts = torch.empty(n, n_samples, device=ro.device) if want_weights else None
     with torch.cuda.device(ro.device):
-        L.check("nerf_b200_render_rays_ex", lib.nerf_b200_render_rays_ex(
-            _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), _ptr(zv), mode,
-            _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(wts), _stream()))
+        if mode == L.FP8:                            # `packed` is the FP8 buffer (pack_weights_fp8)
+            L.check("nerf_b200_render_rays_fp8", lib.nerf_b200_render_rays_fp8(
+                _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), _ptr(zv), _ptr(rgb), _ptr(depth), _ptr(acc),
+                _ptr(wts), _stream()))
+        else:
+            L.check("nerf_b200_render_rays_ex", lib.nerf_b200_render_rays_ex(
+                _ptr(packed), _ptr(ro), _ptr(rd), n, n_samples, near, far, _ptr(tr), _ptr(zv), mode,
+                _ptr(rgb), _ptr(depth), _ptr(acc), _ptr(wts), _stream()))
     out = (rgb, depth) + ((acc,) if want_acc else ()) + ((wts,) if want_weights else ())
     return out
 

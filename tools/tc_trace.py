@@ -11,6 +11,9 @@ z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ck
 net = ops.pack_weights({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev)
 pose = orbit_pose(1, 40)
 TRAIN = len(sys.argv) > 1 and sys.argv[1] == "train"      # timeline of the TRAIN forward variant instead
+FP8 = len(sys.argv) > 1 and sys.argv[1] == "fp8"          # timeline of the FP8-mode kernel
+if FP8:
+    net8 = ops.pack_weights_fp8({k: torch.from_numpy(z[k].astype(np.float32)).to(dev) for k in z.files}, dev, packed=net)
 if TRAIN:
     import nerf_dbr_b200 as nb
     model = nb.NeRFModel().to(dev)
@@ -21,6 +24,9 @@ if TRAIN:
 
     def run():
         ops.train_fwd_bwd(model, ro.to(dev), rd.to(dev), tgt.to(dev), 128, mode=L.BF16)
+elif FP8:
+    def run():
+        ops.render_image(net8, pose, 800, 600, 128, mode=L.FP8)
 else:
     def run():
         ops.render_image(net, pose, 800, 600, 128, mode=1)
