@@ -112,12 +112,18 @@ class B200Renderer(_Base):
         n_rows = height - row0 if n_rows is None else n_rows
         dev = self._torch_device
         with torch.cuda.device(dev):
-            main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
-            sets = []
-            for _ in range(2):
-                sets.append({"rgb": torch.empty(n_rows, width, 3, device=dev), "depth": torch.empty(n_rows, width, device=dev),
-                             "h_rgb": torch.empty(n_rows, width, 3).pin_memory(), "h_depth": torch.empty(n_rows, width).pin_memory(),
-                             "rendered": torch.cuda.Event(), "copied": torch.cuda.Event()})
+            main = torch.cuda.current_stream()
+            # buffer sets, copy stream and events are kept across calls (pinned allocations cost milliseconds)
+            cache = self.__dict__.setdefault("_view_cache", {})
+            key = (n_rows, width)
+            if key not in cache:
+                cache[key] = (torch.cuda.Stream(device=dev),
+                              [{"rgb": torch.empty(n_rows, width, 3, device=dev), "depth": torch.empty(n_rows, width, device=dev),
+                                "h_rgb": torch.empty(n_rows, width, 3).pin_memory(), "h_depth": torch.empty(n_rows, width).pin_memory(),
+                                "rendered": torch.cuda.Event(), "copied": torch.cuda.Event()} for _ in range(2)])
+            side, sets = cache[key]
+            for b in sets:                                               # a previous call's last copies are done before reuse
+                b["copied"].synchronize()
             pending = None
             for i, pose in enumerate(camera_poses):
                 b = sets[i & 1]
