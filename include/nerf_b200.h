@@ -14,9 +14,9 @@
  *     calls cudaMalloc/cudaFree and no data survives a call -> re-entrant across streams and
  *     devices (the launch counter is atomic, the two debug hooks at the end of this header are per
  *     device).  One exception: train_fwd_bwd in BF16 mode creates two auxiliary streams and three
- *     events per device on first use and reuses them (its weight-gradient launches fork onto them
- *     and join back into the caller's stream before the call returns), so training calls for ONE
- *     device must come from one host thread at a time.
+ *     events per (device, caller stream) on first use and reuses them (its weight-gradient launches fork
+ *     onto them and join back into the caller's stream before the call returns; at most 8 caller
+ *     streams per device), so training calls for ONE device must come from one host thread at a time.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *     all work is enqueued asynchronously on it.
  *   - return value: 0 = ok, negative = NERF_B200_E* argument error (nothing was

@@ -366,25 +366,35 @@ static int sm_count()
 // which HBM idles; with two streams the next tensor's CTAs take over SMs as the previous one's drain.  Forked from
 // and joined back into the caller's stream with events, one set per device.
 struct WgradStreams {
+    cudaStream_t caller = nullptr;               // the stream this set forks from (a set is never shared between caller streams)
     cudaStream_t s[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     bool ok = false;
 };
-static WgradStreams *wgrad_streams()
+// One set per (device, caller stream), up to kSetsPerDevice caller streams per device: two training calls that run
+// concurrently on different streams (the coarse and the fine network of a small batch) must not share fork / join events.
+constexpr int kSetsPerDevice = 8;
+static WgradStreams *wgrad_streams(cudaStream_t caller)
 {
-    static WgradStreams per_dev[64];
+    static WgradStreams per_dev[64][kSetsPerDevice];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    WgradStreams &w = per_dev[dev];
-    if (!w.ok) {
-        bool good = cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming) == cudaSuccess;
+    WgradStreams *w = nullptr;
+    for (int i = 0; i < kSetsPerDevice && !w; ++i)
+        if (per_dev[dev][i].ok && per_dev[dev][i].caller == caller) w = &per_dev[dev][i];
+    for (int i = 0; i < kSetsPerDevice && !w; ++i)
+        if (!per_dev[dev][i].ok) w = &per_dev[dev][i];
+    if (!w) return nullptr;                      // more caller streams than sets
+    if (!w->ok) {
+        bool good = cudaEventCreateWithFlags(&w->fork, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < 2 && good; ++i)
-            good = cudaStreamCreateWithFlags(&w.s[i], cudaStreamNonBlocking) == cudaSuccess &&
-                   cudaEventCreateWithFlags(&w.join[i], cudaEventDisableTiming) == cudaSuccess;
+            good = cudaStreamCreateWithFlags(&w->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&w->join[i], cudaEventDisableTiming) == cudaSuccess;
         if (!good) { cudaGetLastError(); return nullptr; }
-        w.ok = true;
+        w->caller = caller;
+        w->ok = true;
     }
-    return &w;
+    return w;
 }
 
 static int chunk_rays(int n_samples)
@@ -496,7 +506,7 @@ int nerf_b200_train_fwd_bwd_ex(const void *packed, const nerf_b200_params *param
         auto row = [&](int r) { return ws + (size_t)r * ch; };
         const int split = std::max(1, std::min(64, (int)(ch / 2048)));
         float *scratch = ws + (size_t)R_TOTAL * ch;
-        WgradStreams *wst = tc ? wgrad_streams() : nullptr;
+        WgradStreams *wst = tc ? wgrad_streams(stream) : nullptr;
         if (tc && !wst) return (int)cudaErrorUnknown;
         cudaError_t ce;
         if (tc) {                                       // fork: both wgrad streams wait for the dgrad chain

@@ -42,7 +42,7 @@ class SyntheticDataset:
         for k, frame in enumerate(frames):
             img = Image.open(os.path.join(data_dir, frame["file_path"] + ".png")).convert("RGBA")
             img = img.resize((self.img_w, self.img_h), Image.LANCZOS)                  # loader.py:45-46: host work, as there
-            staged[k] = torch.from_numpy(np.asarray(img))
+            staged[k] = torch.from_numpy(np.array(img))
             poses.append(np.array(frame["transform_matrix"]))
         with torch.cuda.device(self.device):
             rgba = staged.to(self.device, non_blocking=True)
@@ -97,7 +97,7 @@ def write_standin_dataset(data_dir: str, renderer, n_views: Dict[str, int], img_
         for i in range(count):
             pose = orbit_pose(i, max(count, 1))
             ro, rd = renderer.generate_rays(pose, width, height)
-            rgb, _, acc = ops.render_rays(renderer._net(True), ro.reshape(-1, 3), rd.reshape(-1, 3), samples_per_ray, renderer.mode,
+            rgb, _, acc = ops.render_rays(renderer._net(True, render=True), ro.reshape(-1, 3), rd.reshape(-1, 3), samples_per_ray, renderer.mode,
                                           renderer.near, renderer.far, want_acc=True)
             rgba = torch.cat([rgb, acc[:, None]], dim=-1).clamp(0.0, 1.0).reshape(height, width, 4)
             Image.fromarray((rgba.cpu().numpy() * 255.0 + 0.5).astype(np.uint8), mode="RGBA").save(

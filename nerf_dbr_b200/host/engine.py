@@ -37,6 +37,9 @@ def _dist():
     return None, 0, 1
 
 
+_SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
 class FlatLayout:
     """Offsets of a list of tensors inside one flat fp32 bucket; every tensor starts 16-byte aligned."""
 
@@ -61,11 +64,15 @@ class TrainEngine:
                  near: float = 2.0, far: float = 6.0, mode: int = L.BF16, lr: float = 5e-4, gamma: float = 1.0,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_norm: Optional[float] = None,
                  n_rays_global: Optional[int] = None, use_graph: bool = True, transport: str = "auto",
-                 data_parallel: bool = True):
+                 data_parallel: bool = True, concurrent_passes: Optional[bool] = None):
         """``n_rays``: this rank's share of the batch (static).  ``transport``: 'auto' (NVLink peer memory when the
         process group supports symmetric memory -- through the NVSwitch's in-network reduction when it offers a
         multicast mapping -- else NCCL), 'p2p' (peer loads / stores), 'multimem' (in-switch reduction), 'nccl'.
-        ``data_parallel=False`` ignores an initialised process group (a single-replica engine)."""
+        ``data_parallel=False`` ignores an initialised process group (a single-replica engine).
+        ``concurrent_passes``: run the coarse and the fine network's chains side by side on two streams and disjoint SM
+        sets (a third / two thirds).  Default: only for small per-GPU batches (BF16 mode, under 200k samples), where the
+        fixed cost of every kernel of a chain -- ramp, tail, the small kernels between the big ones -- is what is left;
+        at full batch the passes are bound by HBM and gain nothing from sharing it."""
         self.lib = L.load_library()
         self.coarse, self.fine = coarse, fine
         self.params: List[torch.nn.Parameter] = list(coarse.parameters()) + list(fine.parameters())
@@ -131,6 +138,14 @@ class TrainEngine:
                                                  n_rays_global=self.n_rays_global, near=near, far=far, mode=mode, want_rgb=False,
                                                  slot=which, packed=self._packed_views[which], grad_out=grads, loss_sum=self.loss_slot))
             torch.cuda.synchronize(self.dev)
+        if concurrent_passes is None:
+            concurrent_passes = mode == L.BF16 and self.n_rays * (n_coarse + n_fine) < 200_000
+        self.concurrent_passes = bool(concurrent_passes)
+        # one side stream per device for every engine of the process (the library keeps a set of auxiliary streams per
+        # caller stream, include/nerf_b200.h)
+        if self.concurrent_passes and self.dev not in _SIDE_STREAMS:
+            _SIDE_STREAMS[self.dev] = torch.cuda.Stream(device=self.dev)
+        self._side = _SIDE_STREAMS.get(self.dev) if self.concurrent_passes else None
         self.graph = None
         self.use_graph = use_graph
         self.steps_enqueued = 0
@@ -169,8 +184,18 @@ class TrainEngine:
     # ------------------------------------------------------------------ the step
     def _enqueue(self) -> None:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for tp in self.passes:
-            tp.run()
+        if self.concurrent_passes:
+            main = torch.cuda.current_stream()
+            sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            share = max(1, round(sms * self.n_coarse / (self.n_coarse + self.n_fine)))
+            self._side.wait_stream(main)                                 # fork: the coarse chain on the side stream
+            with torch.cuda.stream(self._side):
+                self.passes[0].run(sm_limit=share)
+            self.passes[1].run(sm_limit=sms - share)
+            main.wait_stream(self._side)                                 # join before the gradient exchange
+        else:
+            for tp in self.passes:
+                tp.run()
         if self.transport == "nccl":
             import torch.distributed as dist
             dist.all_reduce(self.G)

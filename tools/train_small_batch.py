@@ -16,9 +16,12 @@ ro = torch.zeros(rays, 3) + torch.tensor([0.0, 0.0, 4.0])
 rd = torch.nn.functional.normalize(torch.randn(rays, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
 b = [t.to(dev) for t in (ro, rd, torch.rand(rays, 3, generator=g), torch.rand(rays, 64, generator=g))]
 out = {"rays_per_gpu": rays, "global_rays": 4096}
+conc = None if "--auto" in sys.argv else ("--concurrent" in sys.argv)
+out["concurrent_passes"] = conc
 for use_graph in ((False,) if few else (True, False)):
     c, f = seeded_models(5, 30.0, dev)
-    eng = TrainEngine(c, f, rays, 64, 128, mode=L.BF16, lr=5e-4, max_norm=1.0, n_rays_global=4096, use_graph=use_graph, data_parallel=False)
+    eng = TrainEngine(c, f, rays, 64, 128, mode=L.BF16, lr=5e-4, max_norm=1.0, n_rays_global=4096, use_graph=use_graph, data_parallel=False,
+                      concurrent_passes=conc)
     n_warm, n = (2, 3) if few else (10, 100)
     for _ in range(n_warm):
         eng.step(*b)
