@@ -272,7 +272,9 @@ def test_split_phases_equal_single_call(checkpoints, poses):
             assert int(wd.word.item()) == 0
             out.append((float(tp.loss), tp.rgb.cpu(), [p.grad.cpu().double() for p in coarse.parameters()]))
     (l0, c0, g0), (l1, c1, g1) = out
-    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    # the loss is one fp32 atomicAdd per ray (1024 of them into a sum of ~340): the order moves it by ~1e-6 relative;
+    # the per-ray colours below are the bit-exact check
+    assert abs(l0 - l1) <= 5e-6 * abs(l0)
     assert torch.equal(c0, c1)
     for a, b in zip(g0, g1):
         assert float((a - b).norm()) <= 1e-4 * max(float(a.norm()), 1e-20)
