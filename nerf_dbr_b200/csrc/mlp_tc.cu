@@ -86,8 +86,10 @@ constexpr uint32_t SM_DE = SM_RAYB + 8192;                 // [8][32] f32      d
 constexpr uint32_t SM_SCR = SM_DE + 1024;                  // back-warp scratch (256 B)
 constexpr uint32_t SM_BAR = SM_SCR + 256;                  // mbarriers
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t SM_STAGE = SM_TMEM + 256;               // TRAIN: 8 x 2 KB store staging, one per epilogue warp
-constexpr uint32_t SM_TOTAL = SM_STAGE + 16384;
+constexpr uint32_t SM_STAGE = SM_TMEM + 256;               // TRAIN: six 4 KB store staging buffers (epilogue warps 0-5; warps 6, 7 use
+                                                           // the 4 KB tails of weight slots 0 and 1, which no 36 KB stage ever lands in)
+constexpr uint32_t SM_TOTAL = SM_STAGE + 24576;
+static_assert((kStagesPerTile - kStagesC0) % 4 == 2, "the two 36 KB colour-layer-0 stages land in ring slots 2 and 3");
 constexpr uint32_t kSmemBytes = SM_TOTAL + 1024;           // + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -202,9 +204,11 @@ __device__ __forceinline__ void sincos_phase(uint32_t phase, float &s, float &c)
 // front: rays, depths, points, encoded-position tile (bf16, swizzled) and per-ray colour bias
 __device__ __forceinline__ float bf16_hi(float v) { return __uint_as_float(__float_as_uint(__bfloat162float(__float2bfloat16_rn(v)))); }
 
+// pe_bulk (TRAIN): the caller copies the warp's 32 rows of the encoded-position tile to the workspace with one bulk copy
+// (the shared-memory operand tile IS the workspace image of G_PE), so the per-row stores are skipped
 template <int SRC, bool SPLIT, bool TRAIN>
 __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, int rb_buf, int row, float step,
-                             const float *__restrict__ wf)
+                             const float *__restrict__ wf, bool pe_bulk = false)
 {
     RowInfo ri = row_info(a, tile, row);
     if (SRC == SRC_POINTS) ri.valid = tile * kTileM + row < a.n_points;
@@ -236,7 +240,7 @@ __device__ void produce_tile(const Args &a, uint8_t *sm, int tile, int pe_buf, i
     }
     if (TRAIN) {                                           // the bf16 values the MMA sees, [feature][sample] for wgrad
         const int col = ws_col(a, ri);
-        if (col >= 0) {
+        if (col >= 0 && !pe_bulk) {
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = pack_bf16(feat[2 * i], feat[2 * i + 1]);
@@ -443,10 +447,11 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
 
 // ws_out (TRAIN): bf16 operand blocks of the workspace (or nullptr); ws_row = first feature of this warp's 64;
 // col_r / stage: see store_block_rows_staged (train_layout.h); mask_out = this thread's mask word or nullptr
+// col0 >= 0: the warp's rows are the consecutive samples col0 .. col0 + 31 -> TMA store (store_block_rows_bulk)
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
                                               unsigned short *ws_out = nullptr, int ws_row = 0, const int *col_r = nullptr,
-                                              uint32_t stage = 0, unsigned long long *mask_out = nullptr)
+                                              uint32_t stage = 0, unsigned long long *mask_out = nullptr, int col0 = -1)
 {
     uint32_t xa[32], xb[32];
     tmem_ld32(t_cols, xa);
@@ -463,8 +468,14 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_add
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready);
             // exactly what the next layer multiplies: the bf16-rounded values (128 contiguous bytes per sample)
-            const int cr[4] = {col_r[0], col_r[1], col_r[2], col_r[3]};
-            store_block_rows_staged(ws_out, ws_row, cr, pk, stage, lane);
+            if (col0 >= 0) {
+                store_block_rows_bulk<0>(ws_out, ws_row, col0, pk, stage, lane);
+            } else {
+                const int cr[4] = {col_r[0], col_r[1], col_r[2], col_r[3]};
+                if (lane == 0) bulk_store_reads_done();        // an earlier tile's copy may still read the buffer
+                __syncwarp();
+                store_block_rows_staged(ws_out, ws_row, cr, pk, stage, lane);
+            }
             // + the ReLU mask of these 64 activations for the dgrad chain
             if (mask_out) *mask_out = (unsigned long long)relu_mask_word(pk) | ((unsigned long long)relu_mask_word(pk + 16) << 32);
             return;
@@ -830,11 +841,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         uint32_t g = 0;
         for (int t = 0; t < my_tiles; ++t) {
             long long *tr = (a.trace && blockIdx.x == 0 && t < kTraceTiles && ew == 0 && lane == 0) ? a.trace + t * 72 : nullptr;
-            int col = -1, col_r[4] = {-1, -1, -1, -1};
+            int col = -1, col_r[4] = {-1, -1, -1, -1}, col0 = -1;
             if (TRAIN) {
                 col = ws_col(a, row_info(a, tile_begin + t, row));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) col_r[j] = __shfl_sync(0xffffffffu, col, (lane >> 2) + 8 * j);
+                // all 32 rows of the warp valid and consecutive from a multiple of 32 (every full tile when the sample count is
+                // 16, 32, 64 or 128): store through the TMA engine
+                const int c0 = __shfl_sync(0xffffffffu, col, 0);
+                if (c0 >= 0 && (c0 & 31) == 0 && __all_sync(0xffffffffu, col == c0 + lane)) col0 = c0;
             }
             for (int layer = 0; layer < 8; ++layer, ++g) {
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
@@ -853,13 +868,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                     }
                     epilogue_half<SPLIT>(t_lane + hh * 128, sm_base + SM_BIAS + (layer * 256 + hh * 128 + 64 * w2) * 4,
                                          bar(B_AREADY + 2 * hh + w2), lane, ws_out, G_H + layer * 256 + hh * 128 + 64 * w2, col_r,
-                                         sm_base + SM_STAGE + ew * 2048, mask_out);
+                                         ew < 6 ? sm_base + SM_STAGE + ew * 4096 : sm_base + SM_W + (ew - 6) * kStageSlotBytes + kStageBytes,
+                                         mask_out, col0);
                     if (tr && hh == 0) tr[layer * 8 + 4] = clock64();
                 }
                 if (tr) tr[layer * 8 + 5] = clock64();
             }
             ++g;                                    // colour layer 0 (the back warps' epilogue) takes a region turn too
         }
+        if (TRAIN && lane == 0) bulk_store_drain();
     } else if (warp >= 12) {
         // ================================ front / back =======================================
         const int row = (warp - 12) * 32 + lane;
@@ -867,10 +884,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
         auto produce = [&](int t) {
             const int pb = SPLIT ? 0 : (t & 1), pe_use = SPLIT ? t : (t >> 1);
             if (pe_use >= 1) wait_bar(bar(B_PEEMPTY + pb), (pe_use - 1) & 1, a.dbg, 8);
-            produce_tile<SRC, SPLIT, TRAIN>(a, sm, tile_begin + t, pb, t & 1, row, step, wf);
+            int c0 = -1;
+            if (TRAIN) {
+                // whole warp of valid, consecutive samples from a multiple of 32: its 32 rows of the operand tile (4 KB, already
+                // the workspace image: unit u of a row at u ^ (row & 7), and col = row mod 8) go out as ONE bulk copy
+                const int col = ws_col(a, row_info(a, tile_begin + t, row));
+                c0 = __shfl_sync(0xffffffffu, col, 0);
+                if (!(c0 >= 0 && (c0 & 31) == 0 && __all_sync(0xffffffffu, col == c0 + lane))) c0 = -1;
+                if (lane == 0) bulk_store_reads_done();     // the copy issued from this buffer two tiles ago has read it
+                __syncwarp();
+            }
+            produce_tile<SRC, SPLIT, TRAIN>(a, sm, tile_begin + t, pb, t & 1, row, step, wf, c0 >= 0);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_PEFULL + pb));
+            if (lane == 0) {
+                mbar_arrive(bar(B_PEFULL + pb));
+                if (TRAIN && c0 >= 0) {
+                    unsigned short *dst = reinterpret_cast<unsigned short *>(a.ws) + big_row(G_PE, c0);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;"
+                                 ::"l"(dst), "r"(sm_base + SM_PE + pb * 16384 + (warp - 12) * 4096) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
         };
         if (my_tiles > 0) produce(0);
         for (int t = 0; t < my_tiles; ++t) {
@@ -893,6 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
                 composite_tile<SRC>(a, sm, tile_begin + t, row, step, wf, sig_pre, ypre);
             }
         }
+        if (TRAIN && lane == 0) bulk_store_drain();
     }
 
     // ---- teardown ---------------------------------------------------------------------------

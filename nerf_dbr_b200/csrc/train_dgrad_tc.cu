@@ -32,8 +32,9 @@ constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_WC1 = kSlots * kSlotBytes;              // [3][128] f32
 constexpr uint32_t SM_BAR = SM_WC1 + 1536;
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t SM_STAGE = SM_TMEM + 256;                      // 8 x 2 KB store staging, one per epilogue warp
-constexpr uint32_t kSmem = SM_STAGE + 16384 + 1024;
+constexpr uint32_t SM_STAGE = SM_TMEM + 256;                      // 8 x 2 x 4 KB store staging: two buffers per epilogue warp
+constexpr uint32_t kSmem = SM_STAGE + 65536 + 1024;
+static_assert(SM_STAGE % 128 == 0 && kSmem <= 232448, "staging buffers: 128-byte aligned, within the shared memory of an SM");
 
 enum { B_WFULL = 0, B_WEMPTY = 4, B_ACCFULL = 8, B_AREADY = 10, B_R1FREE = 14, B_COUNT = 15 };
 // a_ready[kb]: phase g of a tile = K-block kb of GEMM g's A operand is in TMEM (g = 0: written by the front warps,
@@ -146,6 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                 const int c = (tile_begin + t) * 128 + q * 32 + (lane >> 2) + 8 * j;
                 col_r[j] = c < a.n_samples_total ? c : -1;
             }
+            // a warp whose 32 samples all exist (every warp but those of the last tile) stores through the TMA engine
+            const int col0 = (tile_begin + t) * 128 + q * 32;
+            const bool whole = col0 + 32 <= a.n_samples_total;
+            uint32_t sbuf = 0;
             for (int g = 0; g < kDgGemms; ++g) {
                 const int layer = 7 - g;                                   // dh of trunk layer `layer`
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (g & 1) * 256 + 64 * w2;
@@ -179,7 +184,14 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
                     }
-                    store_block_rows_staged(a.ws, G_DPRE + layer * 256 + n0, col_r, pk, sm_base + SM_STAGE + ew * 2048, lane);
+                    if (whole) {
+                        store_block_rows_bulk(a.ws, G_DPRE + layer * 256 + n0, col0, pk, sm_base + SM_STAGE + ew * 8192 + sbuf * 4096, lane);
+                        sbuf ^= 1u;
+                    } else {
+                        if (lane == 0) bulk_store_reads_done();            // an earlier tile's copies may still read the buffer
+                        __syncwarp();
+                        store_block_rows_staged(a.ws, G_DPRE + layer * 256 + n0, col_r, pk, sm_base + SM_STAGE + ew * 8192, lane);
+                    }
                 }
             }
             // region 1 (G7's accumulator) has been read: the next tile's G0 operand may be written there
@@ -187,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_R1FREE));
         }
+        if (lane == 0) bulk_store_drain();
     } else if (warp >= 12) {
         // ---------------- front: G0's A operand
         const int row = (warp - 12) * 32 + lane;

@@ -95,14 +95,46 @@ __device__ __forceinline__ void store_block_rows_staged(void *ws, int g0, const 
     }
 }
 
+// The same store through the TMA engine, for a warp whose 32 rows are the 32 consecutive samples col0 .. col0 + 31 with
+// col0 a multiple of 32 (every full warp of the training kernels): its rows are 4 KB contiguous in the workspace.  Each
+// lane writes its 128-byte row into a 4 KB staging buffer (unit u of row r at u ^ (r & 7): the workspace image, and
+// conflict-free), one lane hands the buffer to cp.async.bulk shared -> global.  Against the staged version this drops
+// 8 ld.shared + 8 st.global + their address arithmetic per thread, and the L2 sees whole 128-byte lines in 4 KB bursts
+// instead of eight half lines per store instruction.  `stage` must alternate between two buffers of the warp from call
+// to call: before a buffer is rewritten, the copy issued from it two calls ago has finished reading it
+// (wait_group.read 1; bulk groups of a thread complete in order); with a single buffer per warp (kPending = 0) the
+// previous copy must have read it.  The issuing lane is always lane 0: it must run bulk_store_drain() before the kernel ends.
+template <int kPending = 1>
+__device__ __forceinline__ void store_block_rows_bulk(void *ws, int g0, int col0, const uint32_t (&pk)[32], uint32_t stage, int lane)
+{
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+    __syncwarp();
+    const uint32_t wr = stage + lane * 128;
+    const int sw = lane & 7;                                   // (col0 + lane) & 7
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((u ^ sw) << 4)), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                     "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(ws) + big_row(g0, col0);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(dst), "r"(stage) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void bulk_store_drain() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// before a staging buffer is reused by plain stores: no bulk copy of this thread is still reading shared memory
+__device__ __forceinline__ void bulk_store_reads_done() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ReLU mask of 32 post-ReLU activations held as 16 bf16 pairs (all >= +0): pair i's flags land at bit i (even
 // feature) and bit 16 + i (odd feature).  h + 0x7fff carries into bit 15 exactly when h != 0: 3 instructions a pair.
 __device__ __forceinline__ uint32_t relu_mask_word(const uint32_t *pk)
 {
-    uint32_t acc = 0u;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};          // four independent chains: the epilogue is latency-bound, not issue-bound
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc |= ((pk[i] + 0x7fff7fffu) >> (15 - i)) & (0x00010001u << i);
-    return acc;
+    for (int i = 0; i < 16; ++i) acc[i & 3] |= ((pk[i] + 0x7fff7fffu) >> (15 - i)) & (0x00010001u << i);
+    return (acc[0] | acc[1]) | (acc[2] | acc[3]);
 }
 // ... and the AND-mask (0xffff per active half) of pair i: shift the flags to the byte sign bits, replicate them
 __device__ __forceinline__ uint32_t relu_pair_mask(uint32_t word, int i)
