@@ -292,8 +292,9 @@ def train_roofline(precision, n_samples, flop, ms):
     """Step-level roofline of the training workload, per GPU (n_samples, flop: this rank's share).  BF16 mode is HBM-bound by construction: the forward writes the
     bf16 operand blocks (4544 B/sample + 88 B of masks and head rows), the dgrad chain writes dpre (4352 B, reads
     88 B), the eleven wgrad launches read every operand once (9600 B), the ray kernel 36 B -- 18.7 KB per sample
-    (DESIGN.md 4.3).  Pure-write streams top out at 3.9 TB/s on this part (tools/probe/hbm_write_bw.py), reads at
-    6.9 TB/s, so the floor of this traffic mix is about 0.70 of the copy-bandwidth peak reported here."""
+    (DESIGN.md 4.3).  That traffic is what the step is measured against; the part streams writes at 6.2-6.3 TB/s and reads at
+    6.9 TB/s (tools/probe/hbm_store_probe.cu), and what bounds the forward and dgrad kernels below that is the serial chain of
+    their epilogue warps (accumulator -> pack -> stage -> bulk store -> mask per layer half), not HBM."""
     tfl = flop / (ms * 1e-3) / 1e12
     if precision != "bf16":
         return {"bound": "tensor", "achieved": tfl, "peak": peaks()["bf16_tflops"], "unit": "TFLOP/s",
@@ -309,7 +310,8 @@ def train_roofline(precision, n_samples, flop, ms):
             "traffic": traffic, "algorithmic_bytes_per_sample": bytes_per_sample, "tflops": tfl,
             "tflops_frac_of_bf16_peak": tfl / peaks()["bf16_tflops"],
             "note": ("whole step: forward, dgrad chain and wgrad on tcgen05 (bf16 operands, fp32 accumulate); activations and "
-                     "pre-activation gradients visit HBM once as bf16; write-only streams peak at 3.9 TB/s on this part")}
+                     "pre-activation gradients visit HBM once as bf16 (TMA bulk stores); the forward and dgrad kernels are bound by "
+                     "their epilogue warps' per-half chain, wgrad by HBM reads (5.9 TB/s)")}
 
 
 def measure_train(dev, rank, world, weak, steps, warmup, precision, fused=True, transport="auto"):
