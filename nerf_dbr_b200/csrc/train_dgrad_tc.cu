@@ -32,8 +32,9 @@ constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_WC1 = kSlots * kSlotBytes;              // [3][128] f32
 constexpr uint32_t SM_BAR = SM_WC1 + 1536;
 constexpr uint32_t SM_TMEM = SM_BAR + 256;
-constexpr uint32_t SM_STAGE = SM_TMEM + 256;                      // 8 x 2 x 4 KB store staging: two buffers per epilogue warp
-constexpr uint32_t kSmem = SM_STAGE + 65536 + 1024;
+constexpr int kStageBufs = 2;                                     // 4 KB store staging buffers per epilogue warp
+constexpr uint32_t SM_STAGE = SM_TMEM + 256;
+constexpr uint32_t kSmem = SM_STAGE + 8 * kStageBufs * 4096 + 1024;
 static_assert(SM_STAGE % 128 == 0 && kSmem <= 232448, "staging buffers: 128-byte aligned, within the shared memory of an SM");
 
 enum { B_WFULL = 0, B_WEMPTY = 4, B_ACCFULL = 8, B_AREADY = 10, B_R1FREE = 14, B_COUNT = 15 };
@@ -185,12 +186,13 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const Args a)
                         if (lane == 0) mbar_arrive(bar(B_AREADY + 2 * hh + w2));
                     }
                     if (whole) {
-                        store_block_rows_bulk(a.ws, G_DPRE + layer * 256 + n0, col0, pk, sm_base + SM_STAGE + ew * 8192 + sbuf * 4096, lane);
-                        sbuf ^= 1u;
+                        store_block_rows_bulk<kStageBufs - 1>(a.ws, G_DPRE + layer * 256 + n0, col0, pk,
+                                                              sm_base + SM_STAGE + (ew * kStageBufs + sbuf) * 4096, lane);
+                        sbuf = (sbuf + 1u) % kStageBufs;
                     } else {
                         if (lane == 0) bulk_store_reads_done();            // an earlier tile's copies may still read the buffer
                         __syncwarp();
-                        store_block_rows_staged(a.ws, G_DPRE + layer * 256 + n0, col_r, pk, sm_base + SM_STAGE + ew * 8192, lane);
+                        store_block_rows_staged(a.ws, G_DPRE + layer * 256 + n0, col_r, pk, sm_base + SM_STAGE + ew * kStageBufs * 4096, lane);
                     }
                 }
             }
