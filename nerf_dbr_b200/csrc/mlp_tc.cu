@@ -990,7 +990,7 @@ static int cluster_default()
 template <int SRC, bool SPLIT, bool TRAIN = false>
 static int launch(Args &a, cudaStream_t stream)
 {
-    a.pair = TRAIN ? 1 : cluster_default();           // the TRAIN variant is bound by its HBM writes: pairing buys nothing there
+    a.pair = TRAIN ? 1 : cluster_default();           // TRAIN: the paired weight stream measured 3-4 % SLOWER per training step (r2)
     int grid = plan(a);
     if (a.pair > 1 && a.n_tiles < 4 * grid) { a.pair = 1; grid = plan(a); }  // small launches: ghost tiles would dominate
     if (grid < 0) return grid;
