@@ -260,6 +260,16 @@ __device__ __forceinline__ void add2(float &x0, float &x1, float b0, float b1)
         "mov.b64 {%0, %1}, d;\n\t}"
         : "=f"(x0), "=f"(x1) : "f"(x0), "f"(x1), "f"(b0), "f"(b1));
 }
+// (d0, d1) = (a0, a1) * (m, m) + (c0, c1) as one packed fp32x2 FMA (FFMA2): two independent IEEE fused multiply-adds, bit for
+// bit what two fmaf calls give
+__device__ __forceinline__ void fma2_bcast(float &d0, float &d1, float a0, float a1, float m, float c0, float c1)
+{
+    asm("{\n\t.reg .b64 a, mm, c, d;\n\t"
+        "mov.b64 a, {%2, %3};\n\tmov.b64 mm, {%4, %4};\n\tmov.b64 c, {%5, %6};\n\t"
+        "fma.rn.f32x2 d, a, mm, c;\n\t"
+        "mov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(m), "f"(c0), "f"(c1));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
