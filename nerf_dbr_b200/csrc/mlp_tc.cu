@@ -446,7 +446,7 @@ __device__ __forceinline__ void bias_relu_pack_split(const uint32_t (&x)[32], ui
 }
 
 // ws_out (TRAIN): bf16 operand blocks of the workspace (or nullptr); ws_row = first feature of this warp's 64;
-// col_r / stage: see store_block_rows_staged (train_layout.h); mask_out = this thread's mask word or nullptr
+// col_r / stage: see store_block_rows_staged / store_block_rows_bulk (train_layout.h); mask_out = this thread's mask word or nullptr
 // col0 >= 0: the warp's rows are the consecutive samples col0 .. col0 + 31 -> TMA store (store_block_rows_bulk)
 template <bool SPLIT>
 __device__ __forceinline__ void epilogue_half(uint32_t t_cols, uint32_t bias_addr, uint32_t bar_ready, int lane,
