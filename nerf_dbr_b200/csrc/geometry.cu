@@ -96,6 +96,55 @@ __global__ void sample_points_kernel(const float *__restrict__ rays_o,
     }
 }
 
+// Fast path (n_samples % 4 == 0, n_samples <= 1024): a WARP per ray.  The ray's origin and direction are loaded once,
+// its depths sit in shared memory (the uniform table, or a per-warp row of jittered depths), and the 3 S floats of its
+// points leave as lane-contiguous float4 stores (every store instruction writes 512 contiguous bytes) -- no per-element
+// division by the row length and ~25 instructions per 16 bytes, where the flat-stream kernel above spends ~100 and
+// stays instruction-bound at 2.5 TB/s.  Same arithmetic, bit for bit.
+template <bool JITTER>
+__global__ void __launch_bounds__(256) sample_points_rays_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                                                 uint32_t n_rays, uint32_t n_samples, float near, float far,
+                                                                 const float *__restrict__ t_rand, float *__restrict__ points,
+                                                                 float *__restrict__ z_vals)
+{
+    extern __shared__ __align__(16) float z_tab[];   // [S] uniform depths, then (JITTER) 8 per-warp rows of S
+    const float step = linspace_step((int)n_samples);
+    for (uint32_t s = threadIdx.x; s < n_samples; s += blockDim.x)
+        z_tab[s] = depth_uniform((int)s, (int)n_samples, step, near, far);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *zrow = JITTER ? z_tab + (size_t)n_samples * (1 + warp) : z_tab;
+    const uint32_t n_p4 = 3 * n_samples / 4, n_z4 = n_samples / 4;
+    for (uint32_t ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
+        const float o0 = __ldg(rays_o + 3 * (size_t)ray), o1 = __ldg(rays_o + 3 * (size_t)ray + 1), o2 = __ldg(rays_o + 3 * (size_t)ray + 2);
+        const float d0 = __ldg(rays_d + 3 * (size_t)ray), d1 = __ldg(rays_d + 3 * (size_t)ray + 1), d2 = __ldg(rays_d + 3 * (size_t)ray + 2);
+        const size_t base = (size_t)ray * n_samples;
+        if (JITTER) {
+            for (uint32_t s = lane; s < n_samples; s += 32) {
+                float lo = z_tab[s], hi = z_tab[s];
+                if (s > 0) lo = __fmul_rn(0.5f, __fadd_rn(z_tab[s], z_tab[s - 1]));
+                if (s + 1 < n_samples) hi = __fmul_rn(0.5f, __fadd_rn(z_tab[s + 1], z_tab[s]));
+                const float z = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), __ldg(t_rand + base + s)));
+                zrow[s] = z;
+                z_vals[base + s] = z;
+            }
+            __syncwarp();
+        } else {
+            for (uint32_t q = lane; q < n_z4; q += 32)
+                reinterpret_cast<float4 *>(z_vals + base)[q] = reinterpret_cast<const float4 *>(z_tab)[q];
+        }
+        float4 *p4 = reinterpret_cast<float4 *>(points + base * 3);
+        for (uint32_t q = lane; q < n_p4; q += 32) {
+            const uint32_t e = 4 * q, s = e / 3, c = e - 3 * s;        // the float4 starts at component c of sample s
+            const float za = zrow[s], zb = zrow[s + 1 < n_samples ? s + 1 : s];
+            const float a0 = point_on_ray(o0, d0, za), a1 = point_on_ray(o1, d1, za), a2 = point_on_ray(o2, d2, za);
+            const float b0 = point_on_ray(o0, d0, zb), b1 = point_on_ray(o1, d1, zb), b2 = point_on_ray(o2, d2, zb);
+            p4[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
+        }
+        if (JITTER) __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------ importance
 // reference rendering.py:73-95 (+ shape fix); recipe SURVEY A5-A7:
 //   total = torch.sum(w+1e-5): lane l accumulates elements l, l+32, ... ; lanes l, l+8, l+16,
@@ -210,6 +259,39 @@ __global__ void __launch_bounds__(256) encode_kernel(const float *__restrict__ x
     }
 }
 
+// Fast path for a compile-time frequency count (the NeRF configuration: 10 for positions, 4 for directions): a CTA
+// builds the encodings of 64 rows in shared memory as the flat [64][width] image they are in global memory, then copies
+// that image out with lane-contiguous float4 stores.  The row-major kernel above writes sin and cos as 12-byte pieces
+// 24 bytes apart -- two half-covered sectors per piece -- and runs at 2.3 TB/s; the arithmetic here is the same.
+template <int NF>
+__global__ void __launch_bounds__(256) encode_rows_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out)
+{
+    constexpr int W = 3 + 6 * NF, PAIRS = 3 * NF, ROWS = 64;
+    __shared__ __align__(16) float tile[ROWS * W];
+    __shared__ float xin[ROWS * 3];
+    for (size_t row0 = (size_t)blockIdx.x * ROWS; row0 < n; row0 += (size_t)gridDim.x * ROWS) {
+        const int rows = (int)(n - row0 < (size_t)ROWS ? n - row0 : (size_t)ROWS);
+        for (int i = threadIdx.x; i < rows * 3; i += 256) xin[i] = __ldg(x + row0 * 3 + i);
+        __syncthreads();
+        for (int item = threadIdx.x; item < rows * PAIRS; item += 256) {
+            const int r = item / PAIRS, p = item - r * PAIRS, k = p / 3, c = p - 3 * k;
+            const float v = xin[3 * r + c];
+            float *orow = tile + r * W;
+            if (k == 0) orow[c] = v;
+            float sn, cs;
+            sincosf(__fmul_rn(kPiF * (float)(1u << k), v), &sn, &cs);
+            orow[3 + 6 * k + c] = sn;
+            orow[3 + 6 * k + 3 + c] = cs;
+        }
+        __syncthreads();
+        float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 64
+        const int n_f = rows * W, n_f4 = n_f / 4;
+        for (int i = threadIdx.x; i < n_f4; i += 256) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(tile)[i];
+        for (int i = 4 * n_f4 + threadIdx.x; i < n_f; i += 256) dst[i] = tile[i];
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------ compositing
 // One warp per ray; lanes take 32 consecutive samples per step, the transmittance is an
 // exclusive prefix product carried across steps in double (the reference's CPU cumprod keeps
@@ -271,6 +353,73 @@ __global__ void composite_kernel(const float *__restrict__ sigma, const float *_
         cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); cd = warp_sum(cd); ca = warp_sum(ca);
         if (lane == 0) {
             rgb_map[3 * ray + 0] = cr; rgb_map[3 * ray + 1] = cg; rgb_map[3 * ray + 2] = cb;
+            depth[ray] = cd;
+            if (acc) acc[ray] = ca;
+        }
+    }
+}
+
+// Fast path (n_samples % 4 == 0, 16-byte aligned rows): a lane takes FOUR consecutive samples, so a 128-sample ray is
+// one pass: five 16-byte loads per lane, the keep factors of a lane multiplied locally and ONE warp scan per 128
+// samples instead of one per 32 -- the kernel above issues ~150 instructions per 32 samples (two shuffles per double
+// and scan step) and is bound by instruction issue at 3.6 TB/s, not by HBM.  Transmittance = running double product
+// as above (the association of the products differs in the last bit of the DOUBLE, invisible after the fp32 rounding).
+__global__ void __launch_bounds__(256) composite4_kernel(const float *__restrict__ sigma, const float *__restrict__ rgb,
+                                                         const float *__restrict__ z_vals, const float *__restrict__ rays_d,
+                                                         int n_rays, int n_samples, float *__restrict__ rgb_map,
+                                                         float *__restrict__ depth, float *__restrict__ acc,
+                                                         float *__restrict__ weights)
+{
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ray = blockIdx.x * warps + warp; ray < n_rays; ray += gridDim.x * warps) {
+        const float dx = __ldg(rays_d + 3 * (size_t)ray), dy = __ldg(rays_d + 3 * (size_t)ray + 1), dz = __ldg(rays_d + 3 * (size_t)ray + 2);
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        const size_t base = (size_t)ray * n_samples;
+        double carry = 1.0;
+        float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, ca = 0.f;
+        for (int s0 = 0; s0 < n_samples; s0 += 128) {
+            const int s = s0 + 4 * lane;
+            const bool on = s < n_samples;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 z4 = on ? __ldg(reinterpret_cast<const float4 *>(z_vals + base + s)) : zero4;
+            const float4 g4 = on ? __ldg(reinterpret_cast<const float4 *>(sigma + base + s)) : zero4;
+            const float4 c0 = on ? __ldg(reinterpret_cast<const float4 *>(rgb + 3 * (base + s))) : zero4;
+            const float4 c1 = on ? __ldg(reinterpret_cast<const float4 *>(rgb + 3 * (base + s) + 4)) : zero4;
+            const float4 c2 = on ? __ldg(reinterpret_cast<const float4 *>(rgb + 3 * (base + s) + 8)) : zero4;
+            float zn = __shfl_down_sync(0xffffffffu, z4.x, 1);
+            if (lane == 31 && s + 4 < n_samples) zn = __ldg(z_vals + base + s + 4);
+            const float zz[5] = {z4.x, z4.y, z4.z, z4.w, zn};
+            const float sg[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float col[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+            float alpha[4];
+            double pre[4];                                       // product of this lane's keep factors BEFORE sample i
+            double run = 1.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dist = __fmul_rn((s + i + 1 < n_samples) ? __fsub_rn(zz[i + 1], zz[i]) : 1e10f, nrm);
+                alpha[i] = on ? __fsub_rn(1.0f, expf(__fmul_rn(-fmaxf(sg[i], 0.f), dist))) : 0.f;
+                pre[i] = run;
+                run *= on ? (double)__fadd_rn(__fsub_rn(1.0f, alpha[i]), 1e-10f) : 1.0;
+            }
+            const double incl = warp_incl_prod(run, lane);
+            const double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            const double lead = carry * (lane == 0 ? 1.0 : excl);
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
+            float w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                w[i] = __fmul_rn(alpha[i], (float)(lead * pre[i]));
+                cr = fmaf(w[i], col[3 * i + 0], cr);
+                cg = fmaf(w[i], col[3 * i + 1], cg);
+                cb = fmaf(w[i], col[3 * i + 2], cb);
+                cd = fmaf(w[i], zz[i], cd);
+                ca += w[i];
+            }
+            if (weights && on) *reinterpret_cast<float4 *>(weights + base + s) = make_float4(w[0], w[1], w[2], w[3]);
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); cd = warp_sum(cd); ca = warp_sum(ca);
+        if (lane == 0) {
+            rgb_map[3 * (size_t)ray + 0] = cr; rgb_map[3 * (size_t)ray + 1] = cg; rgb_map[3 * (size_t)ray + 2] = cb;
             depth[ray] = cd;
             if (acc) acc[ray] = ca;
         }
@@ -497,6 +646,16 @@ int nerf_b200_sample_points(const float *rays_o, const float *rays_d, int n_rays
     if (!rays_o || !rays_d || !points || !z_vals || n_rays <= 0 || n_samples <= 0) return NERF_B200_EINVAL;
     if (n_samples > 8192) return NERF_B200_EUNSUPPORTED;
     if (((uintptr_t)points | (uintptr_t)z_vals) & 15) return NERF_B200_EALIGN;
+    if (n_samples % 4 == 0 && n_samples <= 1024) {             // warp-per-ray fast path
+        const int grid = grid_for((size_t)n_rays * 32, 256);
+        if (t_rand)
+            sample_points_rays_kernel<true><<<grid, 256, (size_t)n_samples * 9 * sizeof(float), (cudaStream_t)stream>>>(
+                rays_o, rays_d, (uint32_t)n_rays, (uint32_t)n_samples, near, far, t_rand, points, z_vals);
+        else
+            sample_points_rays_kernel<false><<<grid, 256, (size_t)n_samples * sizeof(float), (cudaStream_t)stream>>>(
+                rays_o, rays_d, (uint32_t)n_rays, (uint32_t)n_samples, near, far, t_rand, points, z_vals);
+        return launch_status();
+    }
     size_t units = ((size_t)n_rays * n_samples * 3 + 3) / 4;
     if ((size_t)n_rays * n_samples * 3 + 8 < (1ull << 32) - (size_t)grid_for(units, 256) * 256 * 4)
         sample_points_kernel<uint32_t><<<grid_for(units, 256), 256, n_samples * sizeof(float), (cudaStream_t)stream>>>(
@@ -572,7 +731,12 @@ int nerf_b200_hierarchical_samples(const float *weights, int n_rays, int n_sampl
 int nerf_b200_positional_encoding(const float *x, int64_t n, int n_freq, float *out, void *stream)
 {
     if (!x || !out || n <= 0 || n_freq < 0 || n_freq > 16) return NERF_B200_EINVAL;
-    size_t total = (size_t)n * (3 + 6 * n_freq);
+    if ((n_freq == 10 || n_freq == 4) && ((uintptr_t)out & 15) == 0) {
+        const int grid = grid_for(((size_t)n + 63) / 64 * 256, 256);
+        if (n_freq == 10) encode_rows_kernel<10><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
+        else encode_rows_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
+        return launch_status();
+    }
     int lanes = 4;                                             // smallest power of two >= 3 * n_freq, at most 32
     while (lanes < 3 * n_freq && lanes < 32) lanes <<= 1;
     const int rows = 256 / lanes;
@@ -586,6 +750,11 @@ int nerf_b200_composite(const float *sigma, const float *rgb, const float *z_val
 {
     if (!sigma || !rgb || !z_vals || !rays_d || !rgb_map || !depth || n_rays <= 0 || n_samples <= 0)
         return NERF_B200_EINVAL;
+    if (n_samples % 4 == 0 && (((uintptr_t)sigma | (uintptr_t)rgb | (uintptr_t)z_vals | (uintptr_t)weights) & 15) == 0) {
+        composite4_kernel<<<grid_for((size_t)n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            sigma, rgb, z_vals, rays_d, n_rays, n_samples, rgb_map, depth, acc, weights);
+        return launch_status();
+    }
     composite_kernel<<<grid_for((size_t)n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         sigma, rgb, z_vals, rays_d, n_rays, n_samples, rgb_map, depth, acc, weights);
     return launch_status();
