@@ -259,32 +259,73 @@ __global__ void __launch_bounds__(256) encode_kernel(const float *__restrict__ x
     }
 }
 
-// Fast path for a compile-time frequency count (the NeRF configuration: 10 for positions, 4 for directions): a CTA
-// builds the encodings of 64 rows in shared memory as the flat [64][width] image they are in global memory, then copies
-// that image out with lane-contiguous float4 stores.  The row-major kernel above writes sin and cos as 12-byte pieces
-// 24 bytes apart -- two half-covered sectors per piece -- and runs at 2.3 TB/s; the arithmetic here is the same.
-template <int NF>
-__global__ void __launch_bounds__(256) encode_rows_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out)
+// Fast path for a compile-time frequency count (the NeRF configuration: 10 for positions, 4 for directions).
+//  * Stores: a CTA builds the encodings of 84 rows in shared memory as the flat [84][width] image they are in global
+//    memory and copies that image out with lane-contiguous float4 stores (the row-major kernel above writes sin and cos
+//    as 12-byte pieces 24 bytes apart -- two half-covered sectors per piece -- and runs at 2.3 TB/s).
+//  * Arithmetic: a thread owns one coordinate of one row and ALL its frequencies.  The reference's argument
+//    fl(fl(2^k pi) x) equals 2^k * a with a = fl(pi_f x) (a power of two commutes with the rounding), so one
+//    double-precision product gives a's phase in turns, its fraction goes into a 64-bit fixed-point word, and the phase
+//    of frequency k is a funnel shift of that word: quadrant from the top bits, remainder r in [-pi/4, pi/4], two
+//    degree-7/8 polynomials (cephes sinf / cosf).  ~25 instructions per (sin, cos) pair against ~40 for sincosf with
+//    its own range reduction; |error| <= 1.2e-7 against the exact sin / cos of the reference's fp32 argument (an
+//    emulation over 350 k arguments: 1 ulp against torch's sin / cos, the gate is 3e-7).  |x| > 16384 or NaN: sincosf.
+__device__ __forceinline__ void sincos_quadrant(uint32_t frac, float &sn, float &cs)      // frac: phase in 2^-32 turns
 {
-    constexpr int W = 3 + 6 * NF, PAIRS = 3 * NF, ROWS = 64;
+    const uint32_t t = frac + 0x20000000u;
+    const uint32_t q = t >> 30;
+    const int r32 = (int)(t & 0x3fffffffu) - 0x20000000;
+    const float r = (float)r32 * 1.4629180792671596e-9f;                                  // 2 pi / 2^32
+    const float z = r * r;
+    float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float sr = fmaf(ps * z, r, r);
+    float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    const float cr = fmaf(pc * z, z, fmaf(z, -0.5f, 1.0f));
+    const float s0 = (q & 1u) ? cr : sr, c0 = (q & 1u) ? sr : cr;
+    sn = __int_as_float(__float_as_int(s0) ^ (int)((q & 2u) << 30));
+    cs = __int_as_float(__float_as_int(c0) ^ (int)(((q + 1u) & 2u) << 30));
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256, 6) encode_rows_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out)
+{
+    constexpr int W = 3 + 6 * NF, ROWS = 84;                     // 252 threads: (coordinate, row), rows fastest (no bank conflicts)
     __shared__ __align__(16) float tile[ROWS * W];
     __shared__ float xin[ROWS * 3];
+    const int c = threadIdx.x / ROWS, r = threadIdx.x - c * ROWS;
     for (size_t row0 = (size_t)blockIdx.x * ROWS; row0 < n; row0 += (size_t)gridDim.x * ROWS) {
         const int rows = (int)(n - row0 < (size_t)ROWS ? n - row0 : (size_t)ROWS);
         for (int i = threadIdx.x; i < rows * 3; i += 256) xin[i] = __ldg(x + row0 * 3 + i);
         __syncthreads();
-        for (int item = threadIdx.x; item < rows * PAIRS; item += 256) {
-            const int r = item / PAIRS, p = item - r * PAIRS, k = p / 3, c = p - 3 * k;
+        if (c < 3 && r < rows) {
             const float v = xin[3 * r + c];
-            float *orow = tile + r * W;
-            if (k == 0) orow[c] = v;
-            float sn, cs;
-            sincosf(__fmul_rn(kPiF * (float)(1u << k), v), &sn, &cs);
-            orow[3 + 6 * k + c] = sn;
-            orow[3 + 6 * k + 3 + c] = cs;
+            float *o = tile + r * W + c;
+            o[0] = v;
+            if (fabsf(v) <= 16384.0f) {
+                const double turns = (double)__fmul_rn(kPiF, v) * 0.15915494309189535;
+                const unsigned long long ph = (unsigned long long)__double2ll_rn((turns - rint(turns)) * 9223372036854775808.0);
+                const uint32_t lo = (uint32_t)ph, hi = (uint32_t)(ph >> 32);
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    float sn, cs;
+                    sincos_quadrant(__funnelshift_l(lo, hi, k + 1), sn, cs);
+                    o[3 + 6 * k] = sn;
+                    o[6 + 6 * k] = cs;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    float sn, cs;
+                    sincosf(__fmul_rn(kPiF * (float)(1u << k), v), &sn, &cs);
+                    o[3 + 6 * k] = sn;
+                    o[6 + 6 * k] = cs;
+                }
+            }
         }
         __syncthreads();
-        float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 64
+        float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 84
         const int n_f = rows * W, n_f4 = n_f / 4;
         for (int i = threadIdx.x; i < n_f4; i += 256) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(tile)[i];
         for (int i = 4 * n_f4 + threadIdx.x; i < n_f; i += 256) dst[i] = tile[i];
@@ -596,6 +637,316 @@ __global__ void __launch_bounds__(256) hierarchical_samples_kernel(const float *
     }
 }
 
+// ------------------------------------------------------------------------------ importance / hierarchical, warp per ray
+// Fast paths for n_samples in {32, 64, 128, 256} and up to 256 new samples: ONE WARP owns a ray from its weights to its
+// outputs, so there is no block-wide barrier and no idle warp (the kernels above park seven warps while warp 0 runs the
+// serial prefix sum).  What makes that possible is that the double-precision running sum is usually EXACT: every quotient
+// q = fl((w + 1e-5) / total) that is >= 2^-28 is a multiple of 2^-51, the partial sums stay below 4, so each of them fits the
+// 53-bit significand and ANY order of additions gives the reference's serial result bit for bit -- the warp then uses a
+// parallel scan.  A ray with a quotient outside [2^-28, 2] (negative or enormous weights) takes the serial loop on lane 0.
+// The new samples are sorted in REGISTERS (bitonic network over 32 * NPL elements, shuffles for the strides that cross
+// lanes), the rank merge scatters into a shared-memory row and the row leaves with 16-byte stores; the importance kernel
+// stages its points the same way.  Arithmetic per element is that of the kernels above.
+// number of elements of the SORTED array arr[0 .. 2^LOG) that are <= v (STRICT: < v): a descent with a fixed number of
+// probes and no bounds -- three instructions per probe -- that returns what any correct binary search returns
+template <int LOG, bool STRICT>
+__device__ __forceinline__ int count_below(const float *arr, float v)
+{
+    int pos = 0;
+#pragma unroll
+    for (int step = 1 << (LOG - 1); step > 0; step >>= 1) {
+        const float x = arr[pos + step - 1];
+        if (STRICT ? x < v : x <= v) pos += step;
+    }
+    const float x = arr[pos];
+    if (STRICT ? x < v : x <= v) pos += 1;
+    return pos;
+}
+__device__ __noinline__ int reference_search(const float *cdf, int n, float u)
+{
+    int lo = 0, hi = n;                                          // first index with cdf > u (right = True)
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+template <int PL> struct log2_of_32x { static constexpr int value = PL == 1 ? 5 : PL == 2 ? 6 : PL == 4 ? 7 : 8; };
+
+// returns true when the cdf is non-decreasing (no negative quotient): the searches may then take any probe sequence
+template <int SPL>
+__device__ __forceinline__ bool warp_build_cdf(const float *__restrict__ w, float *cdf, int lane)
+{
+    constexpr int S = 32 * SPL;
+    float v[SPL];
+    float part = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        v[j] = __fadd_rn(__ldg(w + lane + 32 * j), 1e-5f);
+        part = __fadd_rn(part, v[j]);
+    }
+    const float a1 = __shfl_sync(0xffffffffu, part, (lane & 7) + 8);
+    const float a2 = __shfl_sync(0xffffffffu, part, (lane & 7) + 16);
+    const float a3 = __shfl_sync(0xffffffffu, part, (lane & 7) + 24);
+    const float a0 = __shfl_sync(0xffffffffu, part, (lane & 7));
+    const float l8 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+    float total = __shfl_sync(0xffffffffu, l8, 0);
+#pragma unroll
+    for (int l = 1; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, l8, l));
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) cdf[1 + lane + 32 * j] = __fdiv_rn(v[j], total);
+    __syncwarp();
+    float q[SPL];                                                // blocked: lane holds SPL consecutive quotients
+    bool ok = true, nonneg = true;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+        q[i] = cdf[1 + lane * SPL + i];
+        ok = ok && q[i] >= 3.7252902984619140625e-09f && q[i] <= 2.0f;      // 2^-28
+        nonneg = nonneg && q[i] >= 0.0f;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    nonneg = ok || __all_sync(0xffffffffu, nonneg);
+    __syncwarp();
+    if (ok) {
+        double loc[SPL], run = 0.0;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { run += (double)q[i]; loc[i] = run; }
+        double inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const double off = inc - run;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) cdf[1 + lane * SPL + i] = (float)(off + loc[i]);
+        if (lane == 0) cdf[0] = 0.0f;
+    } else if (lane == 0) {
+        double run = 0.0;
+        cdf[0] = 0.0f;
+        for (int s = 1; s <= S; ++s) {
+            run += (double)cdf[s];
+            cdf[s] = (float)run;
+        }
+    }
+    __syncwarp();
+    return nonneg;
+}
+
+// the reference's searchsorted(right=True) + lerp for NPL uniforms at once (the loops of importance_kernel, with a fixed
+// trip count so that the NPL searches interleave)
+template <int SPL, int NPL>
+__device__ __forceinline__ void inverse_cdf(const float *cdf, const float *zs, bool sorted, const float (&uk)[NPL], int (&lo)[NPL], float (&z)[NPL])
+{
+    constexpr int S = 32 * SPL;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) lo[j] = cdf[0] <= uk[j] ? 1 + count_below<log2_of_32x<SPL>::value, false>(cdf + 1, uk[j]) : 0;
+    if (!sorted) {                                               // a non-monotone cdf: the reference's probe sequence decides
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) lo[j] = reference_search(cdf, S + 1, uk[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        const int below = min(max(lo[j] - 1, 0), S - 1), above = min(lo[j], S - 1);
+        float den = __fsub_rn(cdf[above], cdf[below]);
+        if (den < 1e-5f) den = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(uk[j], cdf[below]), den);
+        z[j] = __fadd_rn(zs[below], __fmul_rn(t, __fsub_rn(zs[above], zs[below])));
+    }
+}
+
+// ascending bitonic sort of 32 * NPL floats, element e = lane * NPL + i in register v[i]
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort(float (&v)[NPL], int lane)
+{
+    constexpr int N = 32 * NPL;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= NPL) {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    const int e = lane * NPL + i;
+                    const float o = __shfl_xor_sync(0xffffffffu, v[i], j / NPL);
+                    const bool take_min = ((e & j) == 0) == ((e & k) == 0);
+                    v[i] = take_min ? fminf(v[i], o) : fmaxf(v[i], o);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i)
+                    if ((i & j) == 0) {
+                        const int e = lane * NPL + i;
+                        const bool up = (e & k) == 0;
+                        const float x = v[i], y = v[i | j];
+                        const float mn = fminf(x, y), mx = fmaxf(x, y);
+                        v[i] = up ? mn : mx;
+                        v[i | j] = up ? mx : mn;
+                    }
+            }
+        }
+}
+
+// the 3 n floats of a ray's points out of its depths in shared memory: 16-byte stores when the row allows it
+__device__ __forceinline__ void emit_points_row(float o0, float o1, float o2, float d0, float d1, float d2, const float *zrow, int n,
+                                                float *__restrict__ dst, int lane)
+{
+    if ((n & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
+        float4 *p4 = reinterpret_cast<float4 *>(dst);
+        for (int q = lane; q < 3 * n / 4; q += 32) {
+            const int e = 4 * q, s = e / 3, c = e - 3 * s;
+            const float za = zrow[s], zb = zrow[s + 1 < n ? s + 1 : s];
+            const float a0 = point_on_ray(o0, d0, za), a1 = point_on_ray(o1, d1, za), a2 = point_on_ray(o2, d2, za);
+            const float b0 = point_on_ray(o0, d0, zb), b1 = point_on_ray(o1, d1, zb), b2 = point_on_ray(o2, d2, zb);
+            p4[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
+        }
+    } else {
+        for (int e = lane; e < 3 * n; e += 32) {
+            const int s = e / 3, c = e - 3 * s;
+            dst[e] = point_on_ray(c == 0 ? o0 : c == 1 ? o1 : o2, c == 0 ? d0 : c == 1 ? d1 : d2, zrow[s]);
+        }
+    }
+}
+
+template <int SPL, int NPL>
+__global__ void __launch_bounds__(256) importance_warp_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                                              const float *__restrict__ z_vals, const float *__restrict__ weights,
+                                                              const float *__restrict__ u, int n_rays, int n_new,
+                                                              long long *__restrict__ indices, float *__restrict__ z_new,
+                                                              float *__restrict__ points)
+{
+    constexpr int S = 32 * SPL, NB = 32 * NPL, PITCH = (S + 4) + S + NB;
+    __shared__ __align__(16) float sm[8 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *cdf = sm + warp * PITCH, *zs = cdf + S + 4, *zn = zs + S;
+    for (int ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
+        const bool sorted = warp_build_cdf<SPL>(weights + (size_t)ray * S, cdf, lane);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) zs[lane + 32 * j] = __ldg(z_vals + (size_t)ray * S + lane + 32 * j);
+        float uk[NPL], z[NPL];
+        int lo[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) uk[j] = lane + 32 * j < n_new ? __ldg(u + (size_t)ray * n_new + lane + 32 * j) : 0.0f;
+        __syncwarp();
+        inverse_cdf<SPL, NPL>(cdf, zs, sorted, uk, lo, z);
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int k = lane + 32 * j;
+            if (k < n_new) {
+                indices[(size_t)ray * n_new + k] = lo[j];
+                z_new[(size_t)ray * n_new + k] = z[j];
+                zn[k] = z[j];
+            }
+        }
+        __syncwarp();
+        emit_points_row(__ldg(rays_o + 3 * (size_t)ray), __ldg(rays_o + 3 * (size_t)ray + 1), __ldg(rays_o + 3 * (size_t)ray + 2),
+                        __ldg(rays_d + 3 * (size_t)ray), __ldg(rays_d + 3 * (size_t)ray + 1), __ldg(rays_d + 3 * (size_t)ray + 2), zn, n_new,
+                        points + (size_t)ray * n_new * 3, lane);
+        __syncwarp();
+    }
+}
+
+template <int SPL, int NPL>
+__global__ void __launch_bounds__(256, 4) hierarchical_samples_warp_kernel(const float *__restrict__ weights, const float *__restrict__ t_rand,
+                                                                        const float *__restrict__ u, unsigned long long seed, int n_rays,
+                                                                        int n_new, float near, float far, float *__restrict__ z_out)
+{
+    constexpr int S = 32 * SPL, NB = 32 * NPL, PITCH = (S + NB) + S + NB + (S + 4);
+    __shared__ __align__(16) float sm[8 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *out = sm + warp * PITCH, *a = out + S + NB, *b = a + S, *cdf = b + NB;
+    const float step = linspace_step(S);
+    const int n_out = S + n_new;
+    for (int ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
+        const bool sorted = warp_build_cdf<SPL>(weights + (size_t)ray * S, cdf, lane);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int s = lane + 32 * j;
+            a[s] = t_rand ? depth_jittered(s, S, step, near, far, __ldg(t_rand + (size_t)ray * S + s)) : depth_uniform(s, S, step, near, far);
+        }
+        float uk[NPL], z[NPL];
+        int lo[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int k = lane + 32 * j;
+            uk[j] = 0.0f;
+            if (k < n_new) {
+                if (u) {
+                    uk[j] = __ldg(u + (size_t)ray * n_new + k);
+                } else {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)ray, (uint32_t)(k >> 2), 0u, 0u),
+                                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                    const uint32_t bits = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
+                    uk[j] = (float)(bits >> 8) * 5.9604644775390625e-08f;
+                }
+            }
+        }
+        __syncwarp();
+        inverse_cdf<SPL, NPL>(cdf, a, sorted, uk, lo, z);
+#pragma unroll
+        for (int j = 0; j < NPL; ++j)
+            if (lane + 32 * j >= n_new) z[j] = __int_as_float(0x7f800000);         // +inf pads the sort
+        warp_bitonic_sort<NPL>(z, lane);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) b[lane * NPL + i] = z[i];
+        __syncwarp();
+        // rank merge (merge_samples_kernel): a_i -> i + #{b < a_i}, b_j -> j + #{a <= b_j}; both lists are sorted and b is
+        // padded with +inf to 32 * NPL entries
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float va = a[lane + 32 * j];
+            out[lane + 32 * j + count_below<log2_of_32x<NPL>::value, true>(b, va)] = va;
+        }
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+            if (lane * NPL + i < n_new) out[lane * NPL + i + count_below<log2_of_32x<SPL>::value, false>(a, z[i])] = z[i];
+        __syncwarp();
+        float *dst = z_out + (size_t)ray * n_out;
+        if ((n_out & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
+            for (int q = lane; q < n_out / 4; q += 32) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(out)[q];
+        } else {
+            for (int e = lane; e < n_out; e += 32) dst[e] = out[e];
+        }
+        __syncwarp();
+    }
+}
+
+// merge_samples, warp per ray: the new samples sorted in registers, both lists in shared memory (the sorted one padded
+// with +inf to 2^LOGA entries), fixed-probe rank searches, the union row staged and stored with 16-byte pieces
+template <int LOGA, int NPL>
+__global__ void __launch_bounds__(256) merge_warp_kernel(const float *__restrict__ z_a, const float *__restrict__ z_b, int n_rays, int na,
+                                                         int nb, float *__restrict__ z_out)
+{
+    constexpr int NA = 1 << LOGA, NB = 32 * NPL, PITCH = (NA + NB) + NA + NB;
+    __shared__ __align__(16) float sm[8 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *out = sm + warp * PITCH, *a = out + NA + NB, *b = a + NA;
+    const int n_out = na + nb;
+    const float inf = __int_as_float(0x7f800000);
+    for (int ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
+        for (int i = lane; i < NA; i += 32) a[i] = i < na ? __ldg(z_a + (size_t)ray * na + i) : inf;
+        float v[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) v[j] = lane + 32 * j < nb ? __ldg(z_b + (size_t)ray * nb + lane + 32 * j) : inf;
+        warp_bitonic_sort<NPL>(v, lane);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) b[lane * NPL + i] = v[i];
+        __syncwarp();
+        for (int i = lane; i < na; i += 32) {
+            const float va = a[i];
+            out[i + count_below<log2_of_32x<NPL>::value, true>(b, va)] = va;
+        }
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+            if (lane * NPL + i < nb) out[lane * NPL + i + count_below<LOGA, false>(a, v[i])] = v[i];
+        __syncwarp();
+        float *dst = z_out + (size_t)ray * n_out;
+        if ((n_out & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
+            for (int q = lane; q < n_out / 4; q += 32) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(out)[q];
+        } else {
+            for (int e = lane; e < n_out; e += 32) dst[e] = out[e];
+        }
+        __syncwarp();
+    }
+}
+
 static inline int grid_for(size_t work_items, int block, int per_sm = 8)
 {
     int dev = 0, sms = 148;
@@ -604,6 +955,44 @@ static inline int grid_for(size_t work_items, int block, int per_sm = 8)
     size_t want = (work_items + block - 1) / block;
     size_t cap = (size_t)sms * per_sm;            // a whole number of waves of resident CTAs
     return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+
+template <int SPL>
+static bool launch_importance_warp(int nb, int grid, cudaStream_t st, const float *ro, const float *rd, const float *z, const float *w,
+                                   const float *u, int n_rays, int n_new, long long *idx, float *z_new, float *pts)
+{
+    switch (nb) {
+    case 32: importance_warp_kernel<SPL, 1><<<grid, 256, 0, st>>>(ro, rd, z, w, u, n_rays, n_new, idx, z_new, pts); return true;
+    case 64: importance_warp_kernel<SPL, 2><<<grid, 256, 0, st>>>(ro, rd, z, w, u, n_rays, n_new, idx, z_new, pts); return true;
+    case 128: importance_warp_kernel<SPL, 4><<<grid, 256, 0, st>>>(ro, rd, z, w, u, n_rays, n_new, idx, z_new, pts); return true;
+    case 256: importance_warp_kernel<SPL, 8><<<grid, 256, 0, st>>>(ro, rd, z, w, u, n_rays, n_new, idx, z_new, pts); return true;
+    }
+    return false;
+}
+template <int SPL>
+static bool launch_hierarchical_warp(int nb, int grid, cudaStream_t st, const float *w, const float *t_rand, const float *u,
+                                     unsigned long long seed, int n_rays, int n_new, float near, float far, float *z_out)
+{
+    switch (nb) {
+    case 32: hierarchical_samples_warp_kernel<SPL, 1><<<grid, 256, 0, st>>>(w, t_rand, u, seed, n_rays, n_new, near, far, z_out); return true;
+    case 64: hierarchical_samples_warp_kernel<SPL, 2><<<grid, 256, 0, st>>>(w, t_rand, u, seed, n_rays, n_new, near, far, z_out); return true;
+    case 128: hierarchical_samples_warp_kernel<SPL, 4><<<grid, 256, 0, st>>>(w, t_rand, u, seed, n_rays, n_new, near, far, z_out); return true;
+    case 256: hierarchical_samples_warp_kernel<SPL, 8><<<grid, 256, 0, st>>>(w, t_rand, u, seed, n_rays, n_new, near, far, z_out); return true;
+    }
+    return false;
+}
+
+template <int LOGA>
+static bool launch_merge_warp(int nb, int grid, cudaStream_t st, const float *a, const float *b, int n_rays, int na, int n_new, float *out)
+{
+    switch (nb) {
+    case 32: merge_warp_kernel<LOGA, 1><<<grid, 256, 0, st>>>(a, b, n_rays, na, n_new, out); return true;
+    case 64: merge_warp_kernel<LOGA, 2><<<grid, 256, 0, st>>>(a, b, n_rays, na, n_new, out); return true;
+    case 128: merge_warp_kernel<LOGA, 4><<<grid, 256, 0, st>>>(a, b, n_rays, na, n_new, out); return true;
+    case 256: merge_warp_kernel<LOGA, 8><<<grid, 256, 0, st>>>(a, b, n_rays, na, n_new, out); return true;
+    }
+    return false;
 }
 
 }  // namespace nerfb200
@@ -674,6 +1063,20 @@ int nerf_b200_importance_sample(const float *rays_o, const float *rays_d, const 
         n_rays <= 0 || n_samples <= 0 || n_new <= 0)
         return NERF_B200_EINVAL;
     if (n_samples % 32 != 0 || n_samples > 1024) return NERF_B200_EUNSUPPORTED;
+    if (n_new <= 256 && (n_samples == 32 || n_samples == 64 || n_samples == 128 || n_samples == 256)) {   // warp per ray
+        int nb = 32;
+        while (nb < n_new) nb <<= 1;
+        const int grid = grid_for((size_t)n_rays * 32, 256);
+        cudaStream_t st = (cudaStream_t)stream;
+        long long *idx = (long long *)indices;
+        switch (n_samples) {
+        case 32: launch_importance_warp<1>(nb, grid, st, rays_o, rays_d, z_vals, weights, u, n_rays, n_new, idx, z_new, points); break;
+        case 64: launch_importance_warp<2>(nb, grid, st, rays_o, rays_d, z_vals, weights, u, n_rays, n_new, idx, z_new, points); break;
+        case 128: launch_importance_warp<4>(nb, grid, st, rays_o, rays_d, z_vals, weights, u, n_rays, n_new, idx, z_new, points); break;
+        default: launch_importance_warp<8>(nb, grid, st, rays_o, rays_d, z_vals, weights, u, n_rays, n_new, idx, z_new, points); break;
+        }
+        return launch_status();
+    }
     const int block = 256;                                     // 8 warps share 32 rays per round
     const int group = n_samples <= 384 ? 32 : n_samples <= 768 ? 16 : 8;
     size_t smem = (size_t)group * (2 * n_samples + 3) * sizeof(float);
@@ -692,6 +1095,17 @@ int nerf_b200_merge_samples(const float *z_sorted, const float *z_new, int n_ray
 {
     if (!z_sorted || !z_new || !z_out || n_rays <= 0 || n_sorted <= 0 || n_new <= 0) return NERF_B200_EINVAL;
     if (n_sorted + n_new > 4096) return NERF_B200_EUNSUPPORTED;
+    if (n_sorted <= 256 && n_new <= 256) {                     // warp per ray, sort in registers
+        int nb = 32;
+        while (nb < n_new) nb <<= 1;
+        const int grid = grid_for((size_t)n_rays * 32, 256);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (n_sorted <= 32) launch_merge_warp<5>(nb, grid, st, z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
+        else if (n_sorted <= 64) launch_merge_warp<6>(nb, grid, st, z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
+        else if (n_sorted <= 128) launch_merge_warp<7>(nb, grid, st, z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
+        else launch_merge_warp<8>(nb, grid, st, z_sorted, z_new, n_rays, n_sorted, n_new, z_out);
+        return launch_status();
+    }
     const int block = 128;
     int pow2 = 1;
     while (pow2 < n_new) pow2 <<= 1;
@@ -710,6 +1124,19 @@ int nerf_b200_hierarchical_samples(const float *weights, int n_rays, int n_sampl
 {
     if (!weights || !z_out || n_rays <= 0 || n_samples <= 0 || n_new <= 0) return NERF_B200_EINVAL;
     if (n_samples % 32 != 0 || n_samples > 1024 || n_new > 1024) return NERF_B200_EUNSUPPORTED;
+    if (n_new <= 256 && (n_samples == 32 || n_samples == 64 || n_samples == 128 || n_samples == 256)) {   // warp per ray
+        int nb = 32;
+        while (nb < n_new) nb <<= 1;
+        const int grid = grid_for((size_t)n_rays * 32, 256);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (n_samples) {
+        case 32: launch_hierarchical_warp<1>(nb, grid, st, weights, t_rand, u, seed, n_rays, n_new, near, far, z_out); break;
+        case 64: launch_hierarchical_warp<2>(nb, grid, st, weights, t_rand, u, seed, n_rays, n_new, near, far, z_out); break;
+        case 128: launch_hierarchical_warp<4>(nb, grid, st, weights, t_rand, u, seed, n_rays, n_new, near, far, z_out); break;
+        default: launch_hierarchical_warp<8>(nb, grid, st, weights, t_rand, u, seed, n_rays, n_new, near, far, z_out); break;
+        }
+        return launch_status();
+    }
     int pow2 = 1;
     while (pow2 < n_new) pow2 <<= 1;
     const int block = 256;
@@ -732,7 +1159,8 @@ int nerf_b200_positional_encoding(const float *x, int64_t n, int n_freq, float *
 {
     if (!x || !out || n <= 0 || n_freq < 0 || n_freq > 16) return NERF_B200_EINVAL;
     if ((n_freq == 10 || n_freq == 4) && ((uintptr_t)out & 15) == 0) {
-        const int grid = grid_for(((size_t)n + 63) / 64 * 256, 256);
+        const int rows_per_cta = 84;
+        const int grid = grid_for(((size_t)n + rows_per_cta - 1) / rows_per_cta * 256, 256, 6);
         if (n_freq == 10) encode_rows_kernel<10><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
         else encode_rows_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
         return launch_status();

@@ -93,6 +93,30 @@ def test_importance_sampling_large_random():
         ops.importance_sample(ro.cuda(), rd.cuda(), z[:, :100].contiguous().cuda(), w[:, :100].contiguous().cuda(), u.cuda())
 
 
+@pytest.mark.parametrize("S,N", [(128, 128), (64, 100), (32, 7), (256, 256)])
+def test_importance_sampling_serial_cdf_fallback(S, N):
+    """The warp-per-ray kernels sum the cdf with a parallel scan when every quotient is >= 2^-28 (all partial sums are then
+    exact in double, any order gives the reference's serial result) and fall back to the serial double loop otherwise.
+    Rays with a 3e5 spike have quotients ~3e-11: both branches, interleaved ray by ray, bit-exact against the oracle --
+    for the importance kernel and for the fused sampling kernel (sorted union)."""
+    from nerf_dbr_b200.host import ops
+    g = torch.Generator().manual_seed(S * 1000 + N)
+    R = 3000
+    ro = torch.randn(R, 3, generator=g)
+    rd = torch.randn(R, 3, generator=g)
+    _, z = O.sample_along_rays(ro, rd, S)
+    z = z.contiguous()
+    w = torch.rand(R, S, generator=g) ** 8
+    w[::2, 5] = 3e5
+    w[1::7] = 0.0
+    u = torch.rand(R, N, generator=g)
+    pts_ref, z_ref, idx_ref = O.importance_sample(ro, rd, z, w, u)
+    pts, zn, idx = ops.importance_sample(ro.cuda(), rd.cuda(), z.cuda(), w.cuda(), u.cuda())
+    assert torch.equal(idx.cpu(), idx_ref) and torch.equal(zn.cpu(), z_ref) and torch.equal(pts.cpu(), pts_ref)
+    union = ops.hierarchical_samples(w.cuda(), N, u=u.cuda())
+    assert torch.equal(union.cpu(), torch.sort(torch.cat([z, z_ref], -1), -1).values)
+
+
 def test_positional_encoding():
     from nerf_dbr_b200.host import ops
     g = load_npz("golden_network.npz")
@@ -102,6 +126,25 @@ def test_positional_encoding():
     assert np.array_equal(pe[:, :3], g["pe_pos"][:, :3])                # identity columns: exact
     assert np.abs(pe - g["pe_pos"]).max() <= 3e-7                        # sinf/cosf: <= 2 ulp
     assert np.abs(de - g["pe_dir"]).max() <= 3e-7
+
+
+@pytest.mark.parametrize("n_freq", [10, 4, 6])
+def test_positional_encoding_wide_range(n_freq):
+    """Against the exact sin / cos (float64) of the reference's fp32 argument fl(fl(2^k pi) x): scene-sized, large and
+    huge coordinates (the phase-shift path of the 10- and 4-frequency kernels hands |x| > 16384 to sincosf), ragged row
+    counts around the 84-row tile, and the generic kernel (6 frequencies)."""
+    from nerf_dbr_b200.host import ops
+    g = torch.Generator().manual_seed(n_freq)
+    x = torch.cat([torch.rand(5003, 3, generator=g) * 8 - 4, torch.randn(997, 3, generator=g) * 300,
+                   torch.randn(85, 3, generator=g) * 1e6, torch.tensor([[0.0, 1.0, -1.0], [0.5, 2.0, 4.0], [1e-8, -1e-8, 16384.0]])])
+    got = ops.positional_encoding(x.cuda(), n_freq).cpu()
+    assert got.shape == (x.shape[0], 3 + 6 * n_freq) and torch.equal(got[:, :3], x)
+    for k in range(n_freq):
+        arg = (torch.tensor(2.0 ** k) * torch.pi * x).double()              # fp32 product, as nerf.py:42-43
+        assert (got[:, 3 + 6 * k: 6 + 6 * k].double() - torch.sin(arg)).abs().max() <= 2.5e-7
+        assert (got[:, 6 + 6 * k: 9 + 6 * k].double() - torch.cos(arg)).abs().max() <= 2.5e-7
+    for n in (1, 83, 84, 85, 169):
+        assert torch.equal(ops.positional_encoding(x[:n].cuda(), n_freq).cpu(), got[:n])
 
 
 def test_composite_matches_golden():
