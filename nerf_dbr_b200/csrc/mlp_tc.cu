@@ -543,7 +543,7 @@ __device__ __forceinline__ void color_row(uint32_t t_row, uint32_t rayb_addr, ui
 // colour layer 0's bias for each column on the fly (W_dir [27][128] and b_c0 sit in shared memory, read as
 // broadcasts), relu(acc + bias) . W_c1 -> sigmoid; density = relu(acc col 128 + b).  NeRFModel.forward's outputs.
 __device__ __forceinline__ void query_row(const Args &a, int idx, uint32_t t_row, uint32_t wdir_addr, uint32_t wc1_addr,
-                                          uint32_t bar_c0free, int lane, const float *__restrict__ wf)
+                                          uint32_t bar_c0free, int lane, const float *__restrict__ wf, uint32_t warp_bias_addr)
 {
     float de[kDirFeat];
     const bool on = idx < a.n_points;
@@ -552,6 +552,46 @@ __device__ __forceinline__ void query_row(const Args &a, int idx, uint32_t t_row
         if (on)
 #pragma unroll
             for (int c = 0; c < 3; ++c) d[c] = __ldg(a.dirs + 3 * (size_t)idx + c);
+        // The usual caller passes a ray's direction on every one of its samples (base_renderer.py:165-188 after
+        // sample_points_on_rays): when the warp's 32 rows carry ONE direction, the warp builds that direction's bias row
+        // together -- lane j the j-th encoded feature, lane l columns 4l .. 4l+3, the same fmaf chain per column as the
+        // per-row path below and as the fused render's per-ray bias (so the same bits) -- and the rows take the fused
+        // render's colour head: ~150 instructions per row instead of 1728 packed FMAs + 864 shared-memory reads.
+        const float d0x = __shfl_sync(0xffffffffu, d[0], 0), d0y = __shfl_sync(0xffffffffu, d[1], 0), d0z = __shfl_sync(0xffffffffu, d[2], 0);
+        const bool same = !on || (__float_as_uint(d[0]) == __float_as_uint(d0x) && __float_as_uint(d[1]) == __float_as_uint(d0y) &&
+                                  __float_as_uint(d[2]) == __float_as_uint(d0z));
+        if (__all_sync(0xffffffffu, same)) {
+            float feat = 0.f;
+            if (lane < kDirFeat) {
+                const int w = lane < 3 ? lane : (lane - 3) % 6, c = w % 3;
+                const float dc = c == 0 ? d0x : c == 1 ? d0y : d0z;
+                if (lane < 3) feat = dc;
+                else {
+                    const float arg = __fmul_rn(kPiF * (float)(1 << ((lane - 3) / 6)), dc);
+                    feat = w < 3 ? sinf(arg) : cosf(arg);
+                }
+            }
+            float4 b = ld_shared_f4(wdir_addr + (kDirFeat * 128 + 4 * lane) * 4);    // b_c0
+#pragma unroll
+            for (int j = 0; j < kDirFeat; ++j) {
+                const float dj = __shfl_sync(0xffffffffu, feat, j);
+                const float4 w = ld_shared_f4(wdir_addr + (j * 128 + 4 * lane) * 4);
+                fma2_bcast(b.x, b.y, w.x, w.y, dj, b.x, b.y);
+                fma2_bcast(b.z, b.w, w.z, w.w, dj, b.z, b.w);
+            }
+            st_shared_v4(warp_bias_addr + 16 * lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+            __syncwarp();
+            float r0, r1, r2, sig_pre;
+            color_row(t_row, warp_bias_addr, wc1_addr, bar_c0free, lane, r0, r1, r2, sig_pre);
+            if (on) {
+                a.sigma_out[idx] = fmaxf(sig_pre + __ldg(wf + F_BSIG), 0.f);
+                a.rgb_out[3 * (size_t)idx + 0] = 1.0f / (1.0f + expf(-(r0 + __ldg(wf + F_BC1 + 0))));
+                a.rgb_out[3 * (size_t)idx + 1] = 1.0f / (1.0f + expf(-(r1 + __ldg(wf + F_BC1 + 1))));
+                a.rgb_out[3 * (size_t)idx + 2] = 1.0f / (1.0f + expf(-(r2 + __ldg(wf + F_BC1 + 2))));
+            }
+            __syncwarp();                                   // the bias row is rewritten by this warp's next tile
+            return;
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) de[c] = d[c];
 #pragma unroll
@@ -918,7 +958,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_render_kernel(const Args a)
             const int rpt_shift = a.tiles_per_ray == 1 ? a.s_pad_log2 : 7;
             const uint32_t t_row = tmem_base + ((uint32_t)((warp - 12) * 32) << 16) + (uint32_t)(t & 1) * 256;
             if (SRC == SRC_POINTS) {
-                query_row(a, (tile_begin + t) * kTileM + row, t_row, sm_base + SM_STAGE, sm_base + SM_WC1, bar(B_C0FREE), lane, wf);
+                query_row(a, (tile_begin + t) * kTileM + row, t_row, sm_base + SM_STAGE, sm_base + SM_WC1, bar(B_C0FREE), lane, wf,
+                          sm_base + SM_RAYB + (warp - 12) * 512);
             } else if (TRAIN) {
                 train_heads_row(t_row, sm_base + SM_RAYB + (pb * kMaxRaysPerTile + (row >> rpt_shift)) * 512, sm_base + SM_WC1,
                                 bar(B_C0FREE), lane, wf, a.ws, a.ws_ch, ws_col(a, row_info(a, tile_begin + t, row)));

@@ -165,6 +165,41 @@ def test_query_network_bf16_per_sample_directions(checkpoints, poses):
         assert cmax <= GATE[cname][0] and cmean <= GATE[cname][1], (cname, cmax, cmean)
 
 
+def test_query_network_bf16_shared_direction_rows_equal_the_per_row_path(checkpoints, poses):
+    """A warp whose 32 rows carry one direction (a ray's samples, the reference's usual call) builds the colour-layer-0
+    bias once per warp; rows with their own directions compute it per row.  Same fmaf chain per column -> the same bits:
+    the rows of 300 rays x 32 samples in ray order (every warp uniform) against the same rows interleaved across rays
+    (no warp uniform), un-permuted; plus a ragged tail and a mixed tile."""
+    from nerf_dbr_b200.host import ops
+    from nerf_dbr_b200.host import lib as L
+    net = packed_net(checkpoints["lego"]["fine_model"])
+    ro, rd = O.camera_rays(poses["generic"], 20, 15)
+    ro, rd = ro.reshape(-1, 3).contiguous().cuda(), rd.reshape(-1, 3).contiguous().cuda()
+    S = 32
+    pts, _ = ops.sample_points(ro, rd, S)
+    pos = pts.reshape(-1, 3).contiguous()
+    dirs = rd[:, None, :].expand(-1, S, -1).reshape(-1, 3).contiguous()
+    n = pos.shape[0]
+    perm = torch.arange(n, device="cuda").reshape(-1, S).t().reshape(-1)            # sample-major: neighbours differ in ray
+    with Watchdog() as wd:
+        s_a, c_a = ops.query_network(net, pos, dirs, mode=L.BF16)
+        s_b, c_b = ops.query_network(net, pos[perm].contiguous(), dirs[perm].contiguous(), mode=L.BF16)
+        s_c, c_c = ops.query_network(net, pos[: n - 45].contiguous(), dirs[: n - 45].contiguous(), mode=L.BF16)   # ragged last warp
+        mixed = dirs.clone()
+        mixed[5] = dirs[-1]                                                         # first warp mixed, the rest uniform
+        s_d, c_d = ops.query_network(net, pos, mixed, mode=L.BF16)
+        torch.cuda.synchronize()
+        assert int(wd.word.item()) == 0
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device="cuda")
+    assert torch.equal(s_b[inv], s_a) and torch.equal(c_b[inv], c_a)
+    assert torch.equal(s_c, s_a[: n - 45]) and torch.equal(c_c, c_a[: n - 45])
+    assert torch.equal(s_d[32:], s_a[32:]) and torch.equal(c_d[32:], c_a[32:])
+    keep = torch.ones(32, dtype=torch.bool, device="cuda")
+    keep[5] = False
+    assert torch.equal(c_d[:32][keep], c_a[:32][keep]) and not torch.equal(c_d[5], c_a[5])
+
+
 @pytest.mark.parametrize("S", [64, 100])
 def test_query_network_bf16_then_composite_equals_fused_render(S, checkpoints, poses):
     """The standalone BF16 path (sample_points -> query_network -> composite) and the fused kernel compute the same
