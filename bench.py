@@ -506,7 +506,9 @@ def run_hierarchical(args):
               "roofline": {"bound": "tensor", "achieved": tfl, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tfl / pk["bf16_tflops"],
                            "traffic": None, "kernel": "fused_render_kernel<SRC_RAYS> (coarse + fine passes)",
                            "algorithmic_flop_per_view_rank0": flop_rank,
-                           "sampling_kernel": {"bound": "hbm", "algorithmic_bytes": samp_bytes, "ms": stage[2],
+                           "sampling_kernel": {"bound": "hbm", "limited_by": "instruction issue + shared-memory probes of the sort / rank searches (ncu: issue slots 64 %, "
+                                                             "L1 81 %, DRAM 12 % busy; profiles/r2_hbm_kernels_full_ncu.txt)",
+                                               "algorithmic_bytes": samp_bytes, "ms": stage[2],
                                                "achieved_gbs": samp_bytes / (stage[2] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
                                                "frac": samp_bytes / (stage[2] * 1e-3) / 1e9 / pk["hbm_gbs"]}}})
     if world > 1:
