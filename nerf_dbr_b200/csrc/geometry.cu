@@ -668,9 +668,35 @@ __device__ __noinline__ int reference_search(const float *cdf, int n, float u)
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
     return lo;
 }
+// PL consecutive floats per lane (16-byte aligned rows): vector accesses, no bank conflicts for PL <= 4
+template <int PL>
+__device__ __forceinline__ void ld_blocked(const float *row, int lane, float (&v)[PL])
+{
+    if constexpr (PL == 1) v[0] = row[lane];
+    else if constexpr (PL == 2) { const float2 t = reinterpret_cast<const float2 *>(row)[lane]; v[0] = t.x; v[1] = t.y; }
+    else {
+#pragma unroll
+        for (int h = 0; h < PL / 4; ++h) {
+            const float4 t = reinterpret_cast<const float4 *>(row)[lane * (PL / 4) + h];
+            v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+        }
+    }
+}
+template <int PL>
+__device__ __forceinline__ void st_blocked(float *row, int lane, const float (&v)[PL])
+{
+    if constexpr (PL == 1) row[lane] = v[0];
+    else if constexpr (PL == 2) reinterpret_cast<float2 *>(row)[lane] = make_float2(v[0], v[1]);
+    else {
+#pragma unroll
+        for (int h = 0; h < PL / 4; ++h)
+            reinterpret_cast<float4 *>(row)[lane * (PL / 4) + h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    }
+}
 template <int PL> struct log2_of_32x { static constexpr int value = PL == 1 ? 5 : PL == 2 ? 6 : PL == 4 ? 7 : 8; };
 
-// returns true when the cdf is non-decreasing (no negative quotient): the searches may then take any probe sequence
+// returns true when the cdf is non-decreasing (no negative quotient): the searches may then take any probe sequence.
+// cdf + 1 must be 16-byte aligned (the callers place cdf[0] in the last word of a 16-byte unit).
 template <int SPL>
 __device__ __forceinline__ bool warp_build_cdf(const float *__restrict__ w, float *cdf, int lane)
 {
@@ -695,9 +721,9 @@ __device__ __forceinline__ bool warp_build_cdf(const float *__restrict__ w, floa
     __syncwarp();
     float q[SPL];                                                // blocked: lane holds SPL consecutive quotients
     bool ok = true, nonneg = true;
+    ld_blocked<SPL>(cdf + 1, lane, q);
 #pragma unroll
     for (int i = 0; i < SPL; ++i) {
-        q[i] = cdf[1 + lane * SPL + i];
         ok = ok && q[i] >= 3.7252902984619140625e-09f && q[i] <= 2.0f;      // 2^-28
         nonneg = nonneg && q[i] >= 0.0f;
     }
@@ -716,7 +742,8 @@ __device__ __forceinline__ bool warp_build_cdf(const float *__restrict__ w, floa
         }
         const double off = inc - run;
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) cdf[1 + lane * SPL + i] = (float)(off + loc[i]);
+        for (int i = 0; i < SPL; ++i) q[i] = (float)(off + loc[i]);
+        st_blocked<SPL>(cdf + 1, lane, q);
         if (lane == 0) cdf[0] = 0.0f;
     } else if (lane == 0) {
         double run = 0.0;
@@ -815,7 +842,7 @@ __global__ void __launch_bounds__(256) importance_warp_kernel(const float *__res
     constexpr int S = 32 * SPL, NB = 32 * NPL, PITCH = (S + 4) + S + NB;
     __shared__ __align__(16) float sm[8 * PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *cdf = sm + warp * PITCH, *zs = cdf + S + 4, *zn = zs + S;
+    float *cdf = sm + warp * PITCH + 3, *zs = cdf + S + 1, *zn = zs + S;       // cdf[0] in the last word of a 16-byte unit
     for (int ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
         const bool sorted = warp_build_cdf<SPL>(weights + (size_t)ray * S, cdf, lane);
 #pragma unroll
@@ -851,7 +878,7 @@ __global__ void __launch_bounds__(256, 4) hierarchical_samples_warp_kernel(const
     constexpr int S = 32 * SPL, NB = 32 * NPL, PITCH = (S + NB) + S + NB + (S + 4);
     __shared__ __align__(16) float sm[8 * PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *out = sm + warp * PITCH, *a = out + S + NB, *b = a + S, *cdf = b + NB;
+    float *out = sm + warp * PITCH, *a = out + S + NB, *b = a + S, *cdf = b + NB + 3;
     const float step = linspace_step(S);
     const int n_out = S + n_new;
     for (int ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
@@ -884,8 +911,7 @@ __global__ void __launch_bounds__(256, 4) hierarchical_samples_warp_kernel(const
         for (int j = 0; j < NPL; ++j)
             if (lane + 32 * j >= n_new) z[j] = __int_as_float(0x7f800000);         // +inf pads the sort
         warp_bitonic_sort<NPL>(z, lane);
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) b[lane * NPL + i] = z[i];
+        st_blocked<NPL>(b, lane, z);
         __syncwarp();
         // rank merge (merge_samples_kernel): a_i -> i + #{b < a_i}, b_j -> j + #{a <= b_j}; both lists are sorted and b is
         // padded with +inf to 32 * NPL entries
@@ -926,8 +952,7 @@ __global__ void __launch_bounds__(256) merge_warp_kernel(const float *__restrict
 #pragma unroll
         for (int j = 0; j < NPL; ++j) v[j] = lane + 32 * j < nb ? __ldg(z_b + (size_t)ray * nb + lane + 32 * j) : inf;
         warp_bitonic_sort<NPL>(v, lane);
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) b[lane * NPL + i] = v[i];
+        st_blocked<NPL>(b, lane, v);
         __syncwarp();
         for (int i = lane; i < na; i += 32) {
             const float va = a[i];

@@ -107,3 +107,18 @@ def test_trainer_runs_an_epoch_from_files(tmp_path):
     assert len(tr.train_losses) == 2 and all(math.isfinite(x) for x in tr.train_losses)
     assert os.path.exists(str(tmp_path / "checkpoints" / "checkpoint_epoch_2.pth"))
     assert math.isfinite(tr.validate(data["val"]))
+
+
+def test_composite_white_every_value_pair_and_ragged_sizes():
+    """composite_white against the loader's float64 arithmetic (loader.py:46-54) for EVERY (colour, alpha) byte pair -- the
+    vector kernel forms c / 255 from a product and two fused corrections instead of a division -- and for pixel counts that
+    leave a tail for the scalar kernel."""
+    import numpy as np
+    from nerf_dbr_b200.host import ops
+    c, a = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    rgba = np.stack([c, c[::-1], (c.astype(np.int32) * 7 % 256).astype(np.uint8), a], -1).reshape(-1, 4)      # 65536 pixels
+    img = rgba.astype(np.float64) / 255.0
+    ref = (img[:, :3] * img[:, 3:] + (1.0 - img[:, 3:])).astype(np.float32)
+    for n in (65536, 65535, 4099, 5, 3, 1):
+        out = ops.composite_white(torch.from_numpy(rgba[:n].copy()).cuda())
+        assert out.shape == (n, 3) and np.array_equal(out.cpu().numpy(), ref[:n]), n
