@@ -515,6 +515,54 @@ def run_hierarchical(args):
         dist.destroy_process_group()
 
 
+def measure_hbm_kernels(dev):
+    """"standalone raygen/sampling and standalone compositing -> HBM bandwidth".  The staged API's kernels at the
+    headline shape (800x600x128), inputs resident, CUDA events around 10 launches after 3 warm-ups; outputs (0.7-2 GB each)
+    are larger than the 126 MB L2.  Algorithmic bytes per launch as in SURVEY 8d; peak = the measured copy bandwidth."""
+    import torch
+    from nerf_dbr_b200.host import ops
+    pk = peaks()
+    Wd, Hd, Sd = 800, 600, 128
+    R = Wd * Hd
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+
+    def add(name, ms, nbytes, kernel):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"kernel": kernel, "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / pk["hbm_gbs"]}
+
+    with torch.cuda.device(dev):
+        ro, rd = ops.generate_rays(pose, Wd, Hd, device=dev)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        add("sample_points_on_rays", timed(lambda: ops.sample_points(ro, rd, Sd)), 16 * R * Sd + 24 * R, "sample_points_rays_kernel")
+        _, z = ops.sample_points(ro, rd, Sd)
+        sigma = torch.rand(R, Sd, device=dev)
+        col = torch.rand(R, Sd, 3, device=dev)
+        add("execute_volume_rendering", timed(lambda: ops.composite(sigma, col, z, rd)), 20 * R * Sd + 12 * R + 16 * R, "composite4_kernel")
+        x = torch.rand(1 << 23, 3, device=dev)
+        add("positional_encoding_L10", timed(lambda: ops.positional_encoding(x, 10)), (12 + 4 * 63) * (1 << 23), "encode_rows_kernel<10>")
+        wts = torch.rand(R, Sd, device=dev)
+        u = torch.rand(R, Sd, device=dev)
+        add("importance_sample", timed(lambda: ops.importance_sample(ro, rd, z, wts, u)), (12 + 24) * R * Sd + 24 * R, "importance_warp_kernel")
+    return {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"], "shape": "800x600x128 (encoding: 2^23 points)",
+            "timing": "CUDA events around 10 launches through the tensor-level wrapper (output allocation included), after 3 warm-ups",
+            "kernels": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -695,6 +743,11 @@ def main():
                      "peak_source": pk["source"] + ", burst cuBLAS bf16",
                      "frac_of_sustained": (achieved / pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None},
     }
+    if not args.no_extras:
+        try:
+            extras["hbm_kernels"] = measure_hbm_kernels(dev)
+        except Exception as e:  # noqa: BLE001 -- extras must not take the headline down
+            extras["hbm_kernels"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if extras:
         line["extras"] = extras
     if world == 1 and not args.no_cpu_baseline:
