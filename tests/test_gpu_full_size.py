@@ -99,3 +99,48 @@ def test_full_size_training_step_properties():
     print(f"4096 rays: loss bf16 {l1:.6f} fp32 {l32:.6f}; worst gradient tensors bf16 vs fp32:", [(f"{e:.1e}", k) for e, k in rel[:3]])
     assert abs(l1 - l32) <= 5e-3 * l32
     assert rel[0][0] <= 0.15, rel[0]
+
+
+def test_full_size_sampling_kernels_properties():
+    """configs[4]'s ray count (1600 x 1200 = 1.92 M rays, 128 coarse + 128 importance samples), where the CPU oracle needs
+    minutes: the fused sampling kernel equals the three-stage path (sample_points -> importance_sample -> merge_samples, each
+    pinned to the reference at small sizes) bit for bit; the union is sorted and holds every coarse depth; the staged
+    compositing of the 800x600x128 shape is deterministic and additive over ray shards; the in-kernel uniforms are
+    deterministic per seed."""
+    from nerf_dbr_b200.host import ops
+    dev = torch.device("cuda")
+    R, Sc, Nn = 1600 * 1200, 128, 128
+    g = torch.Generator(device=dev).manual_seed(11)
+    w = torch.rand(R, Sc, device=dev, generator=g) ** 6
+    w[::97] = 0.0                                              # empty rays: uniform pdf from the 1e-5 floor
+    w[5::1013, 17] = 4e5                                       # rays that take the serial cdf path (quotients < 2^-28)
+    u = torch.rand(R, Nn, device=dev, generator=g)
+    ro = torch.zeros(R, 3, device=dev)
+    rd = torch.randn(R, 3, device=dev, generator=g)
+    _, z = ops.sample_points(ro, rd, Sc)
+    assert torch.equal(z, z[:1].expand_as(z))
+    _, z_new, idx = ops.importance_sample(ro, rd, z, w, u)
+    assert int(idx.min()) >= 1 and int(idx.max()) <= Sc + 1
+    ref = ops.merge_samples(z, z_new)
+    del idx
+    out = ops.hierarchical_samples(w, Nn, u=u)
+    assert torch.equal(out, ref)
+    assert bool((out[:, 1:] >= out[:, :-1]).all())
+    # every coarse depth is in the union: removing the new samples' multiset leaves z (checked through sums of exact membership)
+    pos = torch.searchsorted(out, z)                           # first position of each coarse depth in its union row
+    assert bool((torch.gather(out, 1, pos.clamp(max=Sc + Nn - 1)) == z).all())
+    del ref, pos, z_new
+    a, b, c = (ops.hierarchical_samples(w, Nn, seed=s) for s in (3, 3, 4))
+    assert torch.equal(a, b) and not torch.equal(a, c) and bool((a[:, 1:] >= a[:, :-1]).all())
+    del a, b, c, out, u
+    # staged compositing at the headline shape: deterministic, and a shard of the rays gives the bits of the whole
+    R2 = 800 * 600
+    sigma = torch.rand(R2, S, device=dev, generator=g) * 8 - 1
+    col = torch.rand(R2, S, 3, device=dev, generator=g)
+    full = ops.composite(sigma, col, z[:R2], rd[:R2], want_aux=True)
+    again = ops.composite(sigma, col, z[:R2], rd[:R2], want_aux=True)
+    assert all(torch.equal(x, y) for x, y in zip(full, again))
+    lo, hi = 123457, 345679
+    part = ops.composite(sigma[lo:hi], col[lo:hi], z[lo:hi], rd[lo:hi], want_aux=True)
+    assert all(torch.equal(x[lo:hi], y) for x, y in zip(full, part))
+    assert bool(((full[2] >= 0) & (full[2] <= 1 + 1e-5)).all())   # accumulated opacity in [0, 1]
