@@ -291,15 +291,20 @@ __device__ __forceinline__ void sincos_quadrant(uint32_t frac, float &sn, float 
 template <int NF>
 __global__ void __launch_bounds__(256, 6) encode_rows_kernel(const float *__restrict__ x, size_t n, float *__restrict__ out)
 {
-    constexpr int W = 3 + 6 * NF, ROWS = 84;                     // 252 threads: (coordinate, row), rows fastest (no bank conflicts)
+    // 252 threads: (coordinate, row), rows fastest (no bank conflicts); RPT passes of 84 rows per tile, so that a tile is
+    // ~20 KB for either frequency count (three block barriers per tile)
+    constexpr int W = 3 + 6 * NF, RPT = NF == 10 ? 1 : 2, ROWS = 84 * RPT;
     __shared__ __align__(16) float tile[ROWS * W];
     __shared__ float xin[ROWS * 3];
-    const int c = threadIdx.x / ROWS, r = threadIdx.x - c * ROWS;
+    const int c = threadIdx.x / 84, r0 = threadIdx.x - c * 84;
     for (size_t row0 = (size_t)blockIdx.x * ROWS; row0 < n; row0 += (size_t)gridDim.x * ROWS) {
         const int rows = (int)(n - row0 < (size_t)ROWS ? n - row0 : (size_t)ROWS);
         for (int i = threadIdx.x; i < rows * 3; i += 256) xin[i] = __ldg(x + row0 * 3 + i);
         __syncthreads();
-        if (c < 3 && r < rows) {
+#pragma unroll
+        for (int pass = 0; pass < RPT; ++pass) {
+            const int r = r0 + 84 * pass;
+            if (!(c < 3 && r < rows)) continue;
             const float v = xin[3 * r + c];
             float *o = tile + r * W + c;
             o[0] = v;
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(256, 6) encode_rows_kernel(const float *__rest
             }
         }
         __syncthreads();
-        float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 84
+        float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 84 (of 4)
         const int n_f = rows * W, n_f4 = n_f / 4;
         for (int i = threadIdx.x; i < n_f4; i += 256) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(tile)[i];
         for (int i = 4 * n_f4 + threadIdx.x; i < n_f; i += 256) dst[i] = tile[i];
@@ -1184,7 +1189,7 @@ int nerf_b200_positional_encoding(const float *x, int64_t n, int n_freq, float *
 {
     if (!x || !out || n <= 0 || n_freq < 0 || n_freq > 16) return NERF_B200_EINVAL;
     if ((n_freq == 10 || n_freq == 4) && ((uintptr_t)out & 15) == 0) {
-        const int rows_per_cta = 84;
+        const int rows_per_cta = n_freq == 10 ? 84 : 168;
         const int grid = grid_for(((size_t)n + rows_per_cta - 1) / rows_per_cta * 256, 256, 6);
         if (n_freq == 10) encode_rows_kernel<10><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
         else encode_rows_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out);
