@@ -16,3 +16,7 @@ if 'train' in x: print('train', {k:(v.get('ms_per_step'), v.get('value')) for k,
 for k in x:
     if k!='train': print(k, json.dumps(x[k])[:300])
 PY
+# the ncu launch list of the same command (kernel shares; numbers printed under ncu are not bench values)
+if [ "$1" = "--ncu" ]; then
+  S=$(date +%s); timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_under_ncu.json 2> gpurun_out/final_bench_under_ncu.err; echo "ncu launch list rc $? in $(( $(date +%s) - S )) s"; wc -l gpurun_out/final_launches.csv
+fi
