@@ -29,6 +29,26 @@ __global__ void generate_rays_kernel(Pose pose, int width, int row0, int n_rows,
     }
 }
 
+// four consecutive floats of the flat [rays][3] streams per thread (16-byte stores; the rays of a float4 are `ray` and
+// `ray + 1`), same arithmetic: ~25 instructions per float instead of ~80 (two integer divisions per FLOAT above)
+__global__ void __launch_bounds__(256) generate_rays4_kernel(Pose pose, int width, int row0, uint32_t n_quads, float half_w, float half_h,
+                                                             float focal, float4 *__restrict__ rays_o, float4 *__restrict__ rays_d)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
+        const uint32_t e = 4 * q, ray = e / 3, c = e - 3 * ray;
+        int j = row0 + (int)(ray / (uint32_t)width), i = (int)(ray % (uint32_t)width);
+        float dx, dy;
+        pixel_dir(i, j, half_w, half_h, focal, dx, dy);
+        const float a0 = rotate_dir(pose, 0, dx, dy), a1 = rotate_dir(pose, 1, dx, dy), a2 = rotate_dir(pose, 2, dx, dy);
+        if (++i == width) { i = 0; ++j; }
+        pixel_dir(i, j, half_w, half_h, focal, dx, dy);
+        const float b0 = rotate_dir(pose, 0, dx, dy), b1 = rotate_dir(pose, 1, dx, dy), b2 = rotate_dir(pose, 2, dx, dy);
+        const float t0 = pose.t[0], t1 = pose.t[1], t2 = pose.t[2];
+        rays_d[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
+        rays_o[q] = c == 0 ? make_float4(t0, t1, t2, t0) : c == 1 ? make_float4(t1, t2, t0, t1) : make_float4(t2, t0, t1, t2);
+    }
+}
+
 // ------------------------------------------------------------------------------ samples
 // points [R,S,3] as a flat float stream, one float4 (16 B) store per thread-iteration;
 // z_vals [R,S] likewise.  reference base_renderer.py:260-281, rendering.py:17-52
@@ -1052,6 +1072,12 @@ int nerf_b200_generate_rays(const float *c2w_host, int width, int height, float 
         row0 + n_rows > height || !(focal > 0.f))
         return NERF_B200_EINVAL;
     size_t total = (size_t)n_rows * width * 3;
+    if (total % 4 == 0 && total < (1ull << 31) && (((uintptr_t)rays_o | (uintptr_t)rays_d) & 15) == 0) {
+        generate_rays4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+            pose_from_c2w(c2w_host), width, row0, (uint32_t)(total / 4), (float)((double)width * 0.5), (float)((double)height * 0.5), focal,
+            reinterpret_cast<float4 *>(rays_o), reinterpret_cast<float4 *>(rays_d));
+        return launch_status();
+    }
     generate_rays_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         pose_from_c2w(c2w_host), width, row0, n_rows, (float)((double)width * 0.5),
         (float)((double)height * 0.5), focal, rays_o, rays_d);
