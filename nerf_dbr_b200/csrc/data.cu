@@ -113,7 +113,8 @@ int nerf_b200_composite_white(const unsigned char *rgba, int64_t n_pixels, float
         const size_t n4 = (size_t)n_pixels / 4;
         composite_white4_kernel<<<blocks_for(n4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4 *>(rgba), n4, rgb_out);
         done = n4 * 4;
-        if (done == (size_t)n_pixels) return launch_status();
+        const int rc = launch_status();
+        if (rc != 0 || done == (size_t)n_pixels) return rc;
     }
     composite_white_kernel<<<blocks_for((size_t)n_pixels - done), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uchar4 *>(rgba) + done, (size_t)n_pixels - done, rgb_out + 3 * done);
