@@ -17,7 +17,7 @@ for r in rows:
     if metric.startswith("dram__bytes"):
         value *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
     k[name.split("(")[0].split("<")[0]][metric].append(value)
-want = {"generate_rays_kernel": "generate_rays", "sample_points_rays_kernel": ("sample_points", "sample_points_jitter"),
+want = {"generate_rays4_kernel": "generate_rays", "sample_points_rays_kernel": ("sample_points", "sample_points_jitter"),
         "encode_rows_kernel": ("positional_encoding_L10", "positional_encoding_L4"), "composite4_kernel": ("composite", "composite_with_weights"),
         "importance_warp_kernel": "importance_sample", "merge_warp_kernel": "merge_samples",
         "hierarchical_samples_warp_kernel": ("hierarchical_samples_u_given", "hierarchical_samples_philox"),
