@@ -7,7 +7,7 @@
 // Every entry point has a fast kernel for the shapes NeRF uses and keeps its first, shape-agnostic kernel as the fall-back
 // (DESIGN 4.6).  The fast kernels share three rules: a warp -- or a CTA's shared-memory tile -- owns a contiguous piece of
 // the output; every store instruction writes 512 contiguous bytes (lane-contiguous float4); no division or index arithmetic
-// per element.  Measured against the copy peak at 800x600x128: sampling 0.95, compositing 0.86-0.93, encoding 0.82.
+// per element.  Measured against the copy peak at 800x600x128: sampling 0.95, compositing 0.86-0.93, encoding 0.86-0.90.
 #include "common.cuh"
 #include <algorithm>
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const float *__restrict__ x
 
 // Fast path for a compile-time frequency count (the NeRF configuration: 10 for positions, 4 for directions).
 //  * Stores: a CTA builds the encodings of 84 rows in shared memory as the flat [84][width] image they are in global
-//    memory and copies that image out with lane-contiguous float4 stores (the row-major kernel above writes sin and cos
+//    memory and sends that image off as one cp.async.bulk shared -> global copy (the row-major kernel above writes sin and cos
 //    as 12-byte pieces 24 bytes apart -- two half-covered sectors per piece -- and runs at 2.3 TB/s).
 //  * Arithmetic: a thread owns one coordinate of one row and ALL its frequencies.  The reference's argument
 //    fl(fl(2^k pi) x) equals 2^k * a with a = fl(pi_f x) (a power of two commutes with the rounding), so one
@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256, 6) encode_rows_kernel(const float *__rest
     for (size_t row0 = (size_t)blockIdx.x * ROWS; row0 < n; row0 += (size_t)gridDim.x * ROWS) {
         const int rows = (int)(n - row0 < (size_t)ROWS ? n - row0 : (size_t)ROWS);
         for (int i = threadIdx.x; i < rows * 3; i += 256) xin[i] = __ldg(x + row0 * 3 + i);
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous tile's copy has read `tile`
         __syncthreads();
 #pragma unroll
         for (int pass = 0; pass < RPT; ++pass) {
@@ -367,13 +368,26 @@ __global__ void __launch_bounds__(256, 6) encode_rows_kernel(const float *__rest
                 }
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tile written above, visible to the copy engine
         __syncthreads();
         float *dst = out + row0 * W;                           // 16-byte aligned: row0 is a multiple of 84 (of 4)
-        const int n_f = rows * W, n_f4 = n_f / 4;
-        for (int i = threadIdx.x; i < n_f4; i += 256) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(tile)[i];
-        for (int i = 4 * n_f4 + threadIdx.x; i < n_f; i += 256) dst[i] = tile[i];
-        __syncthreads();
+        const int n_f = rows * W;
+        if ((n_f & 3) == 0) {
+            // the whole tile (21 KB) leaves as ONE bulk copy shared -> global issued by one thread: no per-thread copy loop
+            // and no barrier behind it (the wait for its read of `tile` sits at the top of the next iteration, behind the
+            // latency of that tile's input load)
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"((uint32_t)(n_f * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {                                               // ragged last tile
+            const int n_f4 = n_f / 4;
+            for (int i = threadIdx.x; i < n_f4; i += 256) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(tile)[i];
+            for (int i = 4 * n_f4 + threadIdx.x; i < n_f; i += 256) dst[i] = tile[i];
+        }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // `tile` outlives the copy
 }
 
 // ------------------------------------------------------------------------------ compositing
