@@ -39,6 +39,22 @@ def test_row_shards_equal_whole_image(poses):
         assert torch.equal(so, ro[row0:row0 + n]) and torch.equal(sd, rd[row0:row0 + n])
 
 
+@pytest.mark.parametrize("w,h", [(31, 17), (37, 23), (40, 30), (64, 48), (5, 3), (1, 1), (4, 1)])
+def test_generate_rays_both_kernels_bit_exact(w, h, poses):
+    """generate_rays against the oracle for image sizes whose float count is and is not a multiple of four (the float4
+    kernel and the one-float-per-thread kernel), whole images and row bands that start at odd rows."""
+    from nerf_dbr_b200.host import ops
+    for pname in ("generic", "bench0"):
+        ro_ref, rd_ref = O.camera_rays(poses[pname], w, h)
+        ro, rd = ops.generate_rays(poses[pname], w, h)
+        assert torch.equal(ro.cpu(), ro_ref) and torch.equal(rd.cpu(), rd_ref)
+        for row0, n in ((0, h), (1, h - 1), (h // 2, h - h // 2), (h - 1, 1)):
+            if n <= 0:
+                continue
+            so, sd = ops.generate_rays(poses[pname], w, h, row0=row0, n_rows=n)
+            assert torch.equal(so.cpu(), ro_ref[row0:row0 + n]) and torch.equal(sd.cpu(), rd_ref[row0:row0 + n])
+
+
 @pytest.mark.parametrize("n_samples", [1, 2, 7, 16, 33, 64, 100, 128, 192, 256])
 def test_sample_points_bit_exact_any_count(n_samples, poses):
     from nerf_dbr_b200.host import ops
