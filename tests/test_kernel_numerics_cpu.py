@@ -84,3 +84,71 @@ def test_phase_shift_sincos_stays_inside_the_encoding_gate():
         assert np.abs(s - torch.sin(arg).numpy()).max() <= 2.5e-7, k
         assert np.abs(c - torch.cos(arg).numpy()).max() <= 2.5e-7, k
         assert np.abs(s - np.sin(arg.double().numpy())).max() <= 1.3e-7 and np.abs(c - np.cos(arg.double().numpy())).max() <= 1.3e-7, k
+
+
+def _count_below(arr, v, log, strict):
+    """count_below<LOG, STRICT> of csrc/geometry.cu, step for step."""
+    pos = 0
+    step = 1 << (log - 1)
+    while step > 0:
+        x = arr[pos + step - 1]
+        if (x < v) if strict else (x <= v):
+            pos += step
+        step >>= 1
+    x = arr[pos]
+    if (x < v) if strict else (x <= v):
+        pos += 1
+    return pos
+
+
+def test_fixed_probe_descent_equals_searchsorted():
+    """The rank searches of the warp-per-ray sampling kernels: log2(n) + 1 probes without bounds over a sorted row of
+    2^LOG entries (padded with +inf) return numpy's searchsorted for every query, ties and out-of-range values included."""
+    rng = np.random.default_rng(5)
+    for log in (5, 6, 7, 8):
+        n = 1 << log
+        for n_real in (n, n - 1, n // 2 + 3, 1):
+            row = np.sort(rng.integers(0, 40, n_real).astype(np.float32))          # many ties
+            padded = np.concatenate([row, np.full(n - n_real, np.inf, np.float32)])
+            for v in np.concatenate([np.unique(row), np.unique(row) + 0.5, [-1.0, 1e9]]).astype(np.float32):
+                assert _count_below(padded, v, log, False) == np.searchsorted(row, v, side="right")
+                assert _count_below(padded, v, log, True) == np.searchsorted(row, v, side="left")
+
+
+def test_register_bitonic_network_sorts():
+    """warp_bitonic_sort<NPL>: element e = lane * NPL + i, partner e ^ j, ascending blocks where (e & k) == 0 -- the same
+    (k, j) schedule and min/max rule, emulated on whole arrays, sorts every input incl. ties and +inf padding."""
+    rng = np.random.default_rng(6)
+    for npl in (1, 2, 4, 8):
+        n = 32 * npl
+        for trial in range(20):
+            v = rng.integers(0, 50, n).astype(np.float32)
+            v[rng.integers(0, n, 5)] = np.inf
+            ref = np.sort(v)
+            e = np.arange(n)
+            k = 2
+            while k <= n:
+                j = k >> 1
+                while j > 0:
+                    partner = v[e ^ j]
+                    take_min = ((e & j) == 0) == ((e & k) == 0)
+                    v = np.where(take_min, np.minimum(v, partner), np.maximum(v, partner))
+                    j >>= 1
+                k <<= 1
+            assert np.array_equal(v, ref)
+
+
+def test_rank_merge_positions_are_a_permutation():
+    """The rank merge of the sampling kernels: a_i -> i + #{b < a_i}, b_j -> j + #{a <= b_j} fills every slot of the union
+    exactly once and yields sort(cat(a, b)), ties between and inside the lists included."""
+    rng = np.random.default_rng(7)
+    for na, nb in ((128, 128), (64, 100), (32, 7), (96, 1)):
+        a = np.sort(rng.integers(0, 60, na).astype(np.float32))
+        b = np.sort(rng.integers(0, 60, nb).astype(np.float32))
+        out = np.full(na + nb, np.nan, np.float32)
+        pa = np.arange(na) + np.searchsorted(b, a, side="left")
+        pb = np.arange(nb) + np.searchsorted(a, b, side="right")
+        assert len(set(pa) | set(pb)) == na + nb
+        out[pa] = a
+        out[pb] = b
+        assert np.array_equal(out, np.sort(np.concatenate([a, b])))
