@@ -152,3 +152,29 @@ def test_rank_merge_positions_are_a_permutation():
         out[pa] = a
         out[pb] = b
         assert np.array_equal(out, np.sort(np.concatenate([a, b])))
+
+
+def test_compositing_transmittance_association_is_invisible_in_fp32():
+    """composite4_kernel multiplies a lane's four keep factors locally and scans the lane products across the warp; the
+    reference's cumprod is a serial double product.  The two doubles differ in their last bits only, so the fp32
+    transmittance differs at most by one rounding tie: <= 1 ulp, and in well under 1e-4 of the samples."""
+    rng = np.random.default_rng(8)
+    alpha = (rng.random((4000, 128)) ** 3).astype(np.float32)
+    keep = ((np.float32(1.0) - alpha) + np.float32(1e-10)).astype(np.float32).astype(np.float64)
+    serial = np.cumprod(keep, axis=-1)
+    excl_serial = np.concatenate([np.ones_like(serial[:, :1]), serial[:, :-1]], axis=-1).astype(np.float32)
+    blocks = keep.reshape(-1, 32, 4)
+    local_excl = np.concatenate([np.ones_like(blocks[..., :1]), np.cumprod(blocks, axis=-1)[..., :-1]], axis=-1)
+    lane_tot = np.prod(blocks, axis=-1)
+    incl = lane_tot.copy()                                      # Hillis-Steele inclusive scan, as warp_incl_prod
+    o = 1
+    while o < 32:
+        shifted = np.concatenate([np.ones_like(incl[:, :o]), incl[:, :-o]], axis=-1)
+        incl = incl * shifted
+        o <<= 1
+    lead = np.concatenate([np.ones_like(incl[:, :1]), incl[:, :-1]], axis=-1)
+    par = (lead[..., None] * local_excl).reshape(-1, 128).astype(np.float32)
+    diff = par != excl_serial
+    assert diff.mean() < 1e-4
+    ulp = np.abs(par.view(np.int32).astype(np.int64) - excl_serial.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1
